@@ -1,0 +1,161 @@
+/*
+ * vasr_b200.h - C ABI of the B200-native VietASR CTC inference hot path.
+ *
+ * Plain C: opaque handles, raw device/host pointers, sizes.  No torch types.
+ * Every entry point returns 0 on success and a negative vasr_status on
+ * failure; vasr_last_error() gives the thread-local message the host shim
+ * raises as ValueError (VASR_EINVAL) or RuntimeError (everything else).
+ * Unless a function says "host", every data pointer is a DEVICE pointer the
+ * caller owns and keeps alive; work is enqueued on the cudaStream_t passed as
+ * `stream` (a void*, 0 = legacy default stream) and no entry point
+ * synchronises the device except vasr_model_finalize and the *_host calls.
+ * A handle is not internally locked: one handle per module instance per device.
+ *
+ * Activations inside the library are channels-last fp32:
+ *     features [B, T_f, F]   activations [B, T, C]   log-probs [B, T_e, V+1]
+ * i.e. the reference's [B, C, T] tensors transposed (the host shim hands them
+ * back to NeMo-style callers as transposed *views*, no copy).
+ *
+ * Each entry point replaces one reference interface (paths relative to the
+ * dangvansam/viet-asr checkout):
+ *
+ *   vasr_frontend_*      FilterbankFeatures.__init__/forward,
+ *                        nemo/collections/asr/parts/features.py:113-236, 245-301;
+ *                        normalize_batch :17-30; wrapper
+ *                        AudioToMelSpectrogramPreprocessor.forward,
+ *                        nemo/collections/asr/audio_preprocessing.py:78-87, 314-383
+ *   vasr_model_create    JasperEncoder.__init__ + JasperDecoderForCTC.__init__,
+ *                        nemo/collections/asr/jasper.py:136-196, 242-251
+ *   vasr_model_load_tensor / vasr_model_finalize
+ *                        TrainableNM.restore_from -> load_state_dict,
+ *                        nemo/backends/pytorch/nm.py:97-103
+ *   vasr_encoder_forward JasperEncoder.forward, jasper.py:198-204
+ *                        (JasperBlock.forward parts/jasper.py:408-448,
+ *                         MaskedConv1d.forward parts/jasper.py:113-132)
+ *   vasr_decoder_forward JasperDecoderForCTC.forward jasper.py:253-254 +
+ *                        GreedyCTCDecoder.forward greedy_ctc_decoder.py:33-36
+ *   vasr_ctc_collapse    __ctc_decoder_predictions_tensor,
+ *                        nemo/collections/asr/helpers.py:7-33
+ *   vasr_transcribe_host VietASR.transcribe, infer.py:167-171 (greedy wiring,
+ *                        infer.py:113), batched; host buffers in, ids out
+ */
+#ifndef VASR_B200_H
+#define VASR_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VASR_ABI_VERSION 1
+
+typedef enum vasr_status {
+    VASR_OK = 0,
+    VASR_EINVAL = -1,     /* bad argument / unsupported configuration  (ValueError)   */
+    VASR_ECUDA = -2,      /* CUDA runtime / driver error               (RuntimeError) */
+    VASR_ESTATE = -3,     /* call order (e.g. forward before finalize) (RuntimeError) */
+    VASR_ENOMEM = -4      /* workspace too small / allocation failed   (RuntimeError) */
+} vasr_status;
+
+/* precision of the 1x1 (pointwise / residual / final) GEMMs of the encoder */
+typedef enum vasr_gemm_mode {
+    VASR_GEMM_FP32_SIMT = 0,  /* fp32 FMA on CUDA cores (exact-order reference path)          */
+    VASR_GEMM_TF32X3    = 1,  /* tcgen05 kind::tf32, 3-term split: fp32-grade (parity mode)    */
+    VASR_GEMM_TF32X1    = 2   /* tcgen05 kind::tf32, single pass (fast mode, ~5e-4 rel logits) */
+} vasr_gemm_mode;
+
+/* One Jasper block, fields as in the YAML `jasper:` list (jasper.py:27-66). */
+typedef struct vasr_block_cfg {
+    int32_t filters;    /* output channels                                   */
+    int32_t repeat;     /* sub-blocks                                        */
+    int32_t kernel;     /* conv kernel size (odd)                            */
+    int32_t stride;     /* >1 only with dilation == 1                        */
+    int32_t dilation;
+    int32_t residual;   /* 0/1 : 1x1 conv + BN of the block input is added   */
+    int32_t separable;  /* 1: depthwise + pointwise ; 0: plain conv, kernel must be 1 */
+} vasr_block_cfg;
+
+/* Front-end configuration (ctor kwargs of AudioToMelSpectrogramPreprocessor that
+ * matter on the inference path; dither = 0). */
+typedef struct vasr_frontend_cfg {
+    int32_t n_window_size;    /* 320  */
+    int32_t n_window_stride;  /* 160  */
+    int32_t n_fft;            /* 512 (only 512 is built)                     */
+    int32_t nfilt;            /* 64                                          */
+    float   preemph;          /* 0.97                                        */
+    float   log_zero_guard;   /* 2^-24, 'add' guard                          */
+    int32_t pad_to;           /* 0 (infer.py:90) or a positive multiple      */
+} vasr_frontend_cfg;
+
+typedef struct vasr_frontend vasr_frontend;
+typedef struct vasr_model vasr_model;
+
+/* ---- misc ------------------------------------------------------------- */
+int         vasr_abi_version(void);
+const char* vasr_last_error(void);
+/* number of kernels this library has launched in this process (all handles) */
+int64_t     vasr_launch_count(void);
+
+/* ---- front end -------------------------------------------------------- */
+/* window: host float[n_window_size] (torch.hann_window(n, periodic=False));
+ * mel_fb: host float[nfilt * (n_fft/2+1)] row-major (librosa slaney basis). */
+int  vasr_frontend_create(const vasr_frontend_cfg* cfg, const float* window_host,
+                          const float* mel_fb_host, vasr_frontend** out);
+void vasr_frontend_destroy(vasr_frontend* fe);
+/* T_f = 1 + L / hop, then padded up to a multiple of pad_to if pad_to > 0 */
+int  vasr_frontend_num_frames(const vasr_frontend* fe, int64_t L);
+/* wave [B, L] f32, length [B] i64  ->  feat [B, T_f, nfilt] f32 (normalised, masked),
+ * seq_len [B] i64 = ceil(length / hop).  Reflect padding is over the batch-padded row
+ * of L samples, like torch.stft(center=True) on [B, L]; requires L > n_fft/2.        */
+int  vasr_frontend_forward(vasr_frontend* fe, const float* wave, const int64_t* length,
+                           int B, int64_t L, float* feat, int64_t* seq_len, void* stream);
+
+/* ---- acoustic model --------------------------------------------------- */
+int  vasr_model_create(const vasr_block_cfg* blocks, int n_blocks, int feat_in,
+                       int num_classes_with_blank, vasr_model** out);
+void vasr_model_destroy(vasr_model* m);
+/* name = state-dict key ("encoder.3.mconv.1.conv.weight", "decoder_layers.0.bias", ...);
+ * data = fp32, host or device (is_device), dims = shape.  "num_batches_tracked" is ignored. */
+int  vasr_model_load_tensor(vasr_model* m, const char* name, const float* data,
+                            const int64_t* dims, int ndim, int is_device);
+/* folds BatchNorm (eps = 1e-3) into the 1x1 weights, packs operands; errors name the first missing key */
+int  vasr_model_finalize(vasr_model* m, int gemm_mode);
+int  vasr_model_gemm_mode(const vasr_model* m);
+/* T_e for T_f feature frames */
+int  vasr_model_out_frames(const vasr_model* m, int T_f);
+int  vasr_model_out_channels(const vasr_model* m);
+int  vasr_model_num_classes(const vasr_model* m);
+size_t vasr_encoder_workspace_bytes(const vasr_model* m, int B, int T_f);
+
+/* feat [B, T_f, feat_in], seq_len [B] i64 -> enc [B, T_e, C_out] f32 (tail frames NOT
+ * zeroed, like the reference), enc_len [B] f32.  workspace: >= vasr_encoder_workspace_bytes. */
+int  vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
+                          float* enc, float* enc_len, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* enc [B, T_e, C_out] -> log_probs [B, T_e, V+1] f32 (may be NULL), ids [B, T_e] i64 greedy argmax */
+int  vasr_decoder_forward(vasr_model* m, const float* enc, int B, int T_e,
+                          float* log_probs, int64_t* ids, void* stream);
+
+/* GreedyCTCDecoder.forward on foreign log-probs: log_probs [N, V] f32 -> ids [N] i64 (ties -> lowest index) */
+int  vasr_greedy_argmax(const float* log_probs, int N, int V, int64_t* ids, void* stream);
+
+/* ---- greedy CTC collapse ---------------------------------------------- */
+/* ids [B, T] i64 -> out_ids [B, T] i32 (collapsed, -1 padded), out_len [B] i32; all T frames are used */
+int  vasr_ctc_collapse(const int64_t* ids, int B, int T, int blank,
+                       int32_t* out_ids, int32_t* out_len, void* stream);
+
+/* ---- whole path, HOST buffers (the reference-facing plugin call) ------- */
+/* wave_host [B, L] f32 and length_host [B] i64 in (pinned or pageable) host memory;
+ * out_ids_host [B, T_e] i32 (-1 padded) and out_len_host [B] i32 in host memory.
+ * Copies H2D, runs front end -> encoder -> decoder -> collapse, copies D2H, synchronises.
+ * Device scratch is cached inside the model handle and grows on demand.              */
+int  vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const float* wave_host,
+                          const int64_t* length_host, int B, int64_t L,
+                          int32_t* out_ids_host, int32_t* out_len_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VASR_B200_H */

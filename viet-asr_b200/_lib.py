@@ -1,0 +1,91 @@
+"""ctypes binding of libvasr_b200.so (the C ABI declared in include/vasr_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails
+this module raises.  VASR_EINVAL maps to ValueError (the reference raises
+ValueError for bad configuration, e.g. parts/features.py:145,217 and
+parts/jasper.py:61-62), every other status to RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvasr_b200.so")
+
+VASR_OK, VASR_EINVAL, VASR_ECUDA, VASR_ESTATE, VASR_ENOMEM = 0, -1, -2, -3, -4
+GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32X1 = 0, 1, 2
+GEMM_MODES = {"fp32": GEMM_FP32_SIMT, "tf32x3": GEMM_TF32X3, "tf32x1": GEMM_TF32X1}
+
+
+class BlockCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("filters", "repeat", "kernel", "stride", "dilation", "residual", "separable")]
+
+
+class FrontendCfg(C.Structure):
+    _fields_ = [("n_window_size", C.c_int32), ("n_window_stride", C.c_int32), ("n_fft", C.c_int32),
+                ("nfilt", C.c_int32), ("preemph", C.c_float), ("log_zero_guard", C.c_float),
+                ("pad_to", C.c_int32)]
+
+
+# every symbol include/vasr_b200.h declares: (restype, argtypes)
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+PROTOTYPES = {
+    "vasr_abi_version": (_i, []),
+    "vasr_last_error": (C.c_char_p, []),
+    "vasr_launch_count": (_i64, []),
+    "vasr_frontend_create": (_i, [C.POINTER(FrontendCfg), _vp, _vp, C.POINTER(_vp)]),
+    "vasr_frontend_destroy": (None, [_vp]),
+    "vasr_frontend_num_frames": (_i, [_vp, _i64]),
+    "vasr_frontend_forward": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "vasr_model_create": (_i, [C.POINTER(BlockCfg), _i, _i, _i, C.POINTER(_vp)]),
+    "vasr_model_destroy": (None, [_vp]),
+    "vasr_model_load_tensor": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
+    "vasr_model_finalize": (_i, [_vp, _i]),
+    "vasr_model_gemm_mode": (_i, [_vp]),
+    "vasr_model_out_frames": (_i, [_vp, _i]),
+    "vasr_model_out_channels": (_i, [_vp]),
+    "vasr_model_num_classes": (_i, [_vp]),
+    "vasr_encoder_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "vasr_encoder_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "vasr_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "vasr_greedy_argmax": (_i, [_vp, _i, _i, _vp, _vp]),
+    "vasr_ctc_collapse": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "vasr_transcribe_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C viet-asr_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vasr_abi_version() != 1:
+        raise RuntimeError("libvasr_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc == VASR_OK:
+        return
+    msg = load().vasr_last_error().decode("utf-8", "replace")
+    if rc == VASR_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(f"vasr_b200 error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().vasr_launch_count())

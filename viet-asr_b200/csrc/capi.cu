@@ -1,0 +1,454 @@
+// C ABI: model lifecycle (state-dict loading, BatchNorm folding, operand packing), the encoder
+// layer schedule over channels-last activations, decoder, and the host-buffer whole-path call.
+// Interfaces replaced: see include/vasr_b200.h.
+#include "common.cuh"
+#include "kernels.cuh"
+#include <map>
+#include <vector>
+#include <string>
+#include <string.h>
+#include <math.h>
+
+namespace vasr {
+
+std::string& last_error_ref() { static thread_local std::string e; return e; }
+std::atomic<long long> g_launch_count{0};
+
+int set_error(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+struct HostTensor { std::vector<int64_t> dims; std::vector<float> data; };
+
+static inline float round_tf32(float x)
+{
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;   // inf / nan
+    u += 0x1000u;                                      // round to nearest, ties away (cvt.rna.tf32.f32)
+    u &= 0xffffe000u;
+    float r; memcpy(&r, &u, 4);
+    return r;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace vasr
+
+struct vasr_model {
+    std::vector<vasr_block_cfg> blocks;
+    int feat_in = 0, num_classes = 0;
+    std::map<std::string, vasr::HostTensor> host;
+    bool finalized = false;
+    int gemm_mode = VASR_GEMM_FP32_SIMT;
+    std::vector<vasr::SubBlock> layers;
+    std::vector<void*> allocs;
+    int n_stage = 0;
+    int *d_st_k = nullptr, *d_st_s = nullptr, *d_st_d = nullptr, *d_st_p = nullptr;
+    float* d_dec_w = nullptr; float* d_dec_b = nullptr;
+    int out_channels = 0;
+    int cmax = 0;       // widest activation that lives in the workspace
+    // scratch of vasr_transcribe_host (grown on demand)
+    void* scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+namespace vasr {
+
+static int dev_upload(vasr_model* m, const std::vector<float>& h, float** out)
+{
+    float* d = nullptr;
+    VASR_CUDA_OK(cudaMalloc(&d, sizeof(float) * h.size()));
+    m->allocs.push_back(d);
+    VASR_CUDA_OK(cudaMemcpy(d, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
+    *out = d;
+    return VASR_OK;
+}
+
+static int dev_upload_i(vasr_model* m, const std::vector<int>& h, int** out)
+{
+    int* d = nullptr;
+    VASR_CUDA_OK(cudaMalloc(&d, sizeof(int) * (h.size() ? h.size() : 1)));
+    m->allocs.push_back(d);
+    if (!h.empty()) VASR_CUDA_OK(cudaMemcpy(d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
+    *out = d;
+    return VASR_OK;
+}
+
+static int get_tensor(vasr_model* m, const std::string& name, std::initializer_list<int64_t> want,
+                      const HostTensor** out)
+{
+    auto it = m->host.find(name);
+    if (it == m->host.end())
+        return set_error(VASR_EINVAL, "Missing key(s) in state_dict: \"%s\"", name.c_str());
+    const HostTensor& t = it->second;
+    std::vector<int64_t> w(want);
+    bool ok = t.dims.size() == w.size();
+    for (size_t i = 0; ok && i < w.size(); ++i) ok = t.dims[i] == w[i];
+    if (!ok) {
+        std::string got, exp;
+        for (auto d : t.dims) got += std::to_string(d) + ",";
+        for (auto d : w) exp += std::to_string(d) + ",";
+        return set_error(VASR_EINVAL, "size mismatch for %s: checkpoint has [%s] but the model expects [%s]",
+                         name.c_str(), got.c_str(), exp.c_str());
+    }
+    *out = &t;
+    return VASR_OK;
+}
+
+// BatchNorm1d(eps=1e-3) in eval mode -> per-channel (scale, shift)   (parts/jasper.py:392)
+static int bn_fold(vasr_model* m, const std::string& prefix, int c, std::vector<float>& scale, std::vector<float>& shift)
+{
+    const HostTensor *g, *b, *mu, *var;
+    int rc;
+    if ((rc = get_tensor(m, prefix + ".weight", {c}, &g))) return rc;
+    if ((rc = get_tensor(m, prefix + ".bias", {c}, &b))) return rc;
+    if ((rc = get_tensor(m, prefix + ".running_mean", {c}, &mu))) return rc;
+    if ((rc = get_tensor(m, prefix + ".running_var", {c}, &var))) return rc;
+    scale.resize(c); shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+        const double s = (double)g->data[i] / sqrt((double)var->data[i] + 1e-3);
+        scale[i] = (float)s;
+        shift[i] = (float)((double)b->data[i] - (double)mu->data[i] * s);
+    }
+    return VASR_OK;
+}
+
+static int upload_gemm_weight(vasr_model* m, const HostTensor* w, const std::vector<float>& scale, int cout, int cin,
+                              float** d_w, float** d_hi, float** d_lo)
+{
+    std::vector<float> f((size_t)cout * cin), hi(f.size()), lo(f.size());
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i) {
+            const float v = w->data[(size_t)o * cin + i] * scale[o];
+            f[(size_t)o * cin + i] = v;
+            const float h = round_tf32(v);
+            hi[(size_t)o * cin + i] = h;
+            lo[(size_t)o * cin + i] = v - h;
+        }
+    int rc;
+    if ((rc = dev_upload(m, f, d_w))) return rc;
+    if ((rc = dev_upload(m, hi, d_hi))) return rc;
+    if ((rc = dev_upload(m, lo, d_lo))) return rc;
+    return VASR_OK;
+}
+
+}  // namespace vasr
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int vasr_abi_version(void) { return VASR_ABI_VERSION; }
+extern "C" const char* vasr_last_error(void) { return vasr::last_error_ref().c_str(); }
+extern "C" int64_t vasr_launch_count(void) { return (int64_t)vasr::g_launch_count.load(); }
+
+extern "C" int vasr_model_create(const vasr_block_cfg* blocks, int n_blocks, int feat_in,
+                                 int num_classes_with_blank, vasr_model** out)
+{
+    using namespace vasr;
+    VASR_REQUIRE(out && n_blocks >= 0 && (blocks || n_blocks == 0), "vasr_model_create: null block list");
+    VASR_REQUIRE(feat_in > 0 && feat_in % 16 == 0, "vasr_model_create: feat_in must be a positive multiple of 16 (got %d)", feat_in);
+    // 0 = encoder-only handle (no decoder head); n_blocks == 0 = decoder-only handle
+    VASR_REQUIRE(num_classes_with_blank >= 0 && num_classes_with_blank <= 128 && num_classes_with_blank != 1,
+                 "vasr_model_create: num_classes (+blank) must be 0 or in [2, 128] (got %d)", num_classes_with_blank);
+    VASR_REQUIRE(n_blocks > 0 || num_classes_with_blank > 0, "vasr_model_create: neither encoder blocks nor a decoder head");
+    for (int b = 0; b < n_blocks; ++b) {
+        const vasr_block_cfg& c = blocks[b];
+        VASR_REQUIRE(c.filters > 0 && c.filters % 16 == 0, "block %d: filters must be a positive multiple of 16 (got %d)", b, c.filters);
+        VASR_REQUIRE(c.repeat >= 1, "block %d: repeat must be >= 1 (got %d)", b, c.repeat);
+        VASR_REQUIRE(c.kernel >= 1 && c.kernel % 2 == 1, "block %d: kernel must be odd (got %d)", b, c.kernel);
+        VASR_REQUIRE(c.stride >= 1 && c.dilation >= 1, "block %d: stride/dilation must be >= 1", b);
+        // parts/jasper.py:61-62
+        VASR_REQUIRE(!(c.stride > 1 && c.dilation > 1), "Only stride OR dilation may be greater than 1 (block %d)", b);
+        VASR_REQUIRE(c.separable || c.kernel == 1,
+                     "block %d: non-separable blocks are only built for kernel=1 (got %d)", b, c.kernel);
+        VASR_REQUIRE(c.stride == 1 || (c.repeat == 1 && !c.residual && c.separable),
+                     "block %d: a strided block must be separable with repeat=1 and no residual", b);
+    }
+    vasr_model* m = new vasr_model();
+    if (n_blocks > 0) m->blocks.assign(blocks, blocks + n_blocks);
+    m->feat_in = feat_in;
+    m->num_classes = num_classes_with_blank;
+    *out = m;
+    return VASR_OK;
+}
+
+extern "C" void vasr_model_destroy(vasr_model* m)
+{
+    if (!m) return;
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->scratch) cudaFree(m->scratch);
+    delete m;
+}
+
+extern "C" int vasr_model_load_tensor(vasr_model* m, const char* name, const float* data,
+                                      const int64_t* dims, int ndim, int is_device)
+{
+    using namespace vasr;
+    VASR_REQUIRE(m && name && dims && ndim >= 0 && ndim <= 4, "vasr_model_load_tensor: bad argument");
+    const std::string key(name);
+    if (key.size() >= 19 && key.compare(key.size() - 19, 19, "num_batches_tracked") == 0) return VASR_OK;
+    size_t n = 1;
+    HostTensor t;
+    for (int i = 0; i < ndim; ++i) { VASR_REQUIRE(dims[i] >= 0, "negative dim"); t.dims.push_back(dims[i]); n *= (size_t)dims[i]; }
+    VASR_REQUIRE(data || n == 0, "vasr_model_load_tensor: null data for %s", name);
+    t.data.resize(n);
+    if (n) {
+        if (is_device) VASR_CUDA_OK(cudaMemcpy(t.data.data(), data, n * sizeof(float), cudaMemcpyDeviceToHost));
+        else memcpy(t.data.data(), data, n * sizeof(float));
+    }
+    m->host[key] = std::move(t);
+    m->finalized = false;
+    return VASR_OK;
+}
+
+extern "C" int vasr_model_finalize(vasr_model* m, int gemm_mode)
+{
+    using namespace vasr;
+    VASR_REQUIRE(m, "vasr_model_finalize: null model");
+    VASR_REQUIRE(gemm_mode >= VASR_GEMM_FP32_SIMT && gemm_mode <= VASR_GEMM_TF32X1,
+                 "vasr_model_finalize: unknown gemm_mode %d", gemm_mode);
+    for (void* p : m->allocs) cudaFree(p);
+    m->allocs.clear(); m->layers.clear();
+    int rc;
+    std::vector<int> st_k, st_s, st_d, st_p;
+    int cin = m->feat_in, stage = 0, cmax = 0;
+    const int nb = (int)m->blocks.size();
+    for (int b = 0; b < nb; ++b) {
+        const vasr_block_cfg& c = m->blocks[b];
+        const int block_cin = cin;
+        const int per = c.separable ? 5 : 4;
+        int ci = cin;
+        for (int r = 0; r < c.repeat; ++r) {
+            SubBlock sb{};
+            sb.cin = ci; sb.cout = c.filters; sb.kernel = c.kernel; sb.stride = c.stride; sb.dilation = c.dilation;
+            sb.pad = (c.dilation > 1) ? (c.dilation * c.kernel) / 2 - 1 : c.kernel / 2;   // parts/jasper.py:60-65
+            sb.separable = c.separable != 0;
+            sb.relu = true;
+            sb.has_res = (c.residual != 0) && (r == c.repeat - 1);
+            sb.res_cin = block_cin;
+            sb.final_layer = (b == nb - 1) && (r == c.repeat - 1);
+            sb.len_stage_in = stage;
+            const std::string pre = "encoder." + std::to_string(b) + ".mconv.";
+            const HostTensor* w;
+            std::vector<float> scale, shift;
+            if (c.separable) {
+                const HostTensor* dw;
+                if ((rc = get_tensor(m, pre + std::to_string(per * r) + ".conv.weight", {ci, 1, c.kernel}, &dw))) return rc;
+                if ((rc = get_tensor(m, pre + std::to_string(per * r + 1) + ".conv.weight", {c.filters, ci, 1}, &w))) return rc;
+                if ((rc = bn_fold(m, pre + std::to_string(per * r + 2), c.filters, scale, shift))) return rc;
+                std::vector<float> dwt((size_t)c.kernel * ci);
+                for (int ch = 0; ch < ci; ++ch)
+                    for (int k = 0; k < c.kernel; ++k) dwt[(size_t)k * ci + ch] = dw->data[(size_t)ch * c.kernel + k];
+                if ((rc = dev_upload(m, dwt, &sb.dw_w))) return rc;
+                if (c.stride > 1) {
+                    st_k.push_back(c.kernel); st_s.push_back(c.stride); st_d.push_back(c.dilation); st_p.push_back(sb.pad);
+                    ++stage;
+                }
+            } else {
+                if ((rc = get_tensor(m, pre + std::to_string(per * r) + ".conv.weight", {c.filters, ci, 1}, &w))) return rc;
+                if ((rc = bn_fold(m, pre + std::to_string(per * r + 1), c.filters, scale, shift))) return rc;
+            }
+            sb.len_stage_out = stage;
+            if ((rc = upload_gemm_weight(m, w, scale, c.filters, ci, &sb.pw_w, &sb.pw_hi, &sb.pw_lo))) return rc;
+            if (sb.has_res) {
+                const HostTensor* wr;
+                std::vector<float> rscale, rshift;
+                const std::string rp = "encoder." + std::to_string(b) + ".res.0.";
+                if ((rc = get_tensor(m, rp + "0.conv.weight", {c.filters, block_cin, 1}, &wr))) return rc;
+                if ((rc = bn_fold(m, rp + "1", c.filters, rscale, rshift))) return rc;
+                if ((rc = upload_gemm_weight(m, wr, rscale, c.filters, block_cin, &sb.res_w, &sb.res_hi, &sb.res_lo))) return rc;
+                for (int i = 0; i < c.filters; ++i) shift[i] += rshift[i];
+            }
+            if ((rc = dev_upload(m, shift, &sb.shift))) return rc;
+            if (!sb.final_layer) cmax = std::max(cmax, sb.cout);
+            cmax = std::max(cmax, sb.cin);
+            m->layers.push_back(sb);
+            ci = c.filters;
+        }
+        cin = c.filters;
+    }
+    m->out_channels = cin;
+    m->cmax = cmax;
+    m->n_stage = stage;
+    if ((rc = dev_upload_i(m, st_k, &m->d_st_k))) return rc;
+    if ((rc = dev_upload_i(m, st_s, &m->d_st_s))) return rc;
+    if ((rc = dev_upload_i(m, st_d, &m->d_st_d))) return rc;
+    if ((rc = dev_upload_i(m, st_p, &m->d_st_p))) return rc;
+    m->d_dec_w = m->d_dec_b = nullptr;
+    if (m->num_classes > 0) {
+        const HostTensor *dw, *db;
+        if ((rc = get_tensor(m, "decoder_layers.0.weight", {m->num_classes, cin, 1}, &dw))) return rc;
+        if ((rc = get_tensor(m, "decoder_layers.0.bias", {m->num_classes}, &db))) return rc;
+        if ((rc = dev_upload(m, dw->data, &m->d_dec_w))) return rc;
+        if ((rc = dev_upload(m, db->data, &m->d_dec_b))) return rc;
+    }
+    if (gemm_mode != VASR_GEMM_FP32_SIMT) {
+        if ((rc = tc_init())) return rc;
+        for (const SubBlock& sb : m->layers)
+            VASR_REQUIRE(subblock_tc_supported(sb),
+                         "tcgen05 path: sub-block (cin=%d cout=%d k=%d s=%d d=%d) is not a built shape",
+                         sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
+    }
+    m->gemm_mode = gemm_mode;
+    m->finalized = true;
+    VASR_CUDA_OK(cudaDeviceSynchronize());
+    return VASR_OK;
+}
+
+extern "C" int vasr_model_gemm_mode(const vasr_model* m) { return m ? m->gemm_mode : -1; }
+
+extern "C" int vasr_model_out_frames(const vasr_model* m, int T_f)
+{
+    if (!m || T_f <= 0) return vasr::set_error(VASR_EINVAL, "vasr_model_out_frames: bad argument");
+    int t = T_f;
+    for (const vasr_block_cfg& c : m->blocks) {
+        const int pad = (c.dilation > 1) ? (c.dilation * c.kernel) / 2 - 1 : c.kernel / 2;
+        for (int r = 0; r < c.repeat; ++r) t = (t + 2 * pad - c.dilation * (c.kernel - 1) - 1) / c.stride + 1;
+    }
+    return t;
+}
+
+extern "C" int vasr_model_out_channels(const vasr_model* m)
+{
+    if (!m) return -1;
+    return m->blocks.empty() ? m->feat_in : m->blocks.back().filters;
+}
+extern "C" int vasr_model_num_classes(const vasr_model* m) { return m ? m->num_classes : -1; }
+
+extern "C" size_t vasr_encoder_workspace_bytes(const vasr_model* m, int B, int T_f)
+{
+    if (!m || !m->finalized || B <= 0 || T_f <= 0) return 0;
+    // 3 rotating activation buffers + 1 depthwise buffer, each [B, T_f, cmax] worst case
+    // (T never grows along the stack), + the length table
+    const size_t act = vasr::align_up((size_t)B * T_f * m->cmax * sizeof(float), 256);
+    const size_t lens = vasr::align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
+    return lens + 4 * act;
+}
+
+extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
+                                    float* enc, float* enc_len, void* workspace, size_t workspace_bytes,
+                                    void* stream)
+{
+    using namespace vasr;
+    VASR_REQUIRE(m && feat && seq_len && enc && workspace, "vasr_encoder_forward: null argument");
+    if (!m->finalized) return set_error(VASR_ESTATE, "vasr_encoder_forward: weights not finalized (restore_from first)");
+    if (m->blocks.empty()) return set_error(VASR_ESTATE, "vasr_encoder_forward: this handle was created without encoder blocks");
+    VASR_REQUIRE(B > 0 && T_f > 0, "vasr_encoder_forward: B and T must be positive (got %d, %d)", B, T_f);
+    const size_t need = vasr_encoder_workspace_bytes(m, B, T_f);
+    if (workspace_bytes < need)
+        return set_error(VASR_ENOMEM, "vasr_encoder_forward: workspace %zu < required %zu bytes", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    int* lens = (int*)ws;
+    const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
+    const size_t act = align_up((size_t)B * T_f * m->cmax * sizeof(float), 256);
+    float* P[3] = {(float*)(ws + lens_b), (float*)(ws + lens_b + act), (float*)(ws + lens_b + 2 * act)};
+    float* DW = (float*)(ws + lens_b + 3 * act);
+    int rc;
+    if ((rc = launch_lens((const long long*)seq_len, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
+                          lens, enc_len, st))) return rc;
+
+    const float* cur = feat;
+    const float* block_in = feat;
+    int T = T_f;
+    size_t li = 0;
+    for (size_t b = 0; b < m->blocks.size(); ++b) {
+        const vasr_block_cfg& c = m->blocks[b];
+        block_in = cur;
+        for (int r = 0; r < c.repeat; ++r, ++li) {
+            const SubBlock& sb = m->layers[li];
+            const int T_out = (T + 2 * sb.pad - sb.dilation * (sb.kernel - 1) - 1) / sb.stride + 1;
+            float* out = nullptr;
+            if (sb.final_layer) out = enc;
+            else
+                for (int q = 0; q < 3; ++q)
+                    if (P[q] != cur && P[q] != block_in) { out = P[q]; break; }
+            const int* len_in = lens + (size_t)sb.len_stage_in * B;
+            const int* len_out = lens + (size_t)sb.len_stage_out * B;
+            const float* res = sb.has_res ? block_in : nullptr;
+            if (m->gemm_mode != VASR_GEMM_FP32_SIMT) {
+                if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
+                                             m->gemm_mode == VASR_GEMM_TF32X3, st))) return rc;
+            } else {
+                const float* gin = cur;
+                if (sb.separable) {
+                    if ((rc = launch_dw_conv(cur, sb.dw_w, DW, B, sb.cin, T, T_out, sb.kernel, sb.stride,
+                                             sb.dilation, sb.pad, len_in, len_out, st))) return rc;
+                    gin = DW;
+                }
+                if ((rc = launch_pw_gemm(gin, sb.pw_w, sb.cin, res, sb.res_w, sb.res_cin, sb.shift, out, B, T_out,
+                                         sb.cout, len_out, sb.relu ? 1 : 0, sb.final_layer ? 0 : 1, st))) return rc;
+            }
+            cur = out;
+            T = T_out;
+        }
+    }
+    return VASR_OK;
+}
+
+extern "C" int vasr_decoder_forward(vasr_model* m, const float* enc, int B, int T_e,
+                                    float* log_probs, int64_t* ids, void* stream)
+{
+    using namespace vasr;
+    VASR_REQUIRE(m && enc, "vasr_decoder_forward: null argument");
+    if (!m->finalized) return set_error(VASR_ESTATE, "vasr_decoder_forward: weights not finalized (restore_from first)");
+    if (!m->d_dec_w) return set_error(VASR_ESTATE, "vasr_decoder_forward: this handle was created without a decoder head");
+    VASR_REQUIRE(B > 0 && T_e > 0, "vasr_decoder_forward: B and T must be positive (got %d, %d)", B, T_e);
+    return launch_decoder(enc, m->d_dec_w, m->d_dec_b, m->out_channels, m->num_classes, B * T_e, log_probs,
+                          (long long*)ids, (cudaStream_t)stream);
+}
+
+extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const float* wave_host,
+                                    const int64_t* length_host, int B, int64_t L,
+                                    int32_t* out_ids_host, int32_t* out_len_host, void* stream)
+{
+    using namespace vasr;
+    VASR_REQUIRE(fe && m && wave_host && length_host && out_ids_host && out_len_host, "vasr_transcribe_host: null argument");
+    if (!m->finalized) return set_error(VASR_ESTATE, "vasr_transcribe_host: weights not finalized");
+    if (m->blocks.empty() || !m->d_dec_w) return set_error(VASR_ESTATE, "vasr_transcribe_host: needs a handle with encoder and decoder");
+    VASR_REQUIRE(B > 0, "vasr_transcribe_host: batch must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T_f = vasr_frontend_num_frames(fe, L);
+    if (T_f < 0) return T_f;
+    const int T_e = vasr_model_out_frames(m, T_f);
+    const int C = m->out_channels;
+    const size_t ws_b = vasr_encoder_workspace_bytes(m, B, T_f);
+    // scratch layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_wave = take((size_t)B * L * sizeof(float));
+    const size_t o_len = take((size_t)B * sizeof(int64_t));
+    const size_t o_feat = take((size_t)B * T_f * m->feat_in * sizeof(float));
+    const size_t o_seq = take((size_t)B * sizeof(int64_t));
+    const size_t o_enc = take((size_t)B * T_e * C * sizeof(float));
+    const size_t o_elen = take((size_t)B * sizeof(float));
+    const size_t o_ids = take((size_t)B * T_e * sizeof(int64_t));
+    const size_t o_oid = take((size_t)B * T_e * sizeof(int32_t));
+    const size_t o_olen = take((size_t)B * sizeof(int32_t));
+    const size_t o_ws = take(ws_b);
+    if (off > m->scratch_bytes) {
+        VASR_CUDA_OK(cudaStreamSynchronize(st));
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr; m->scratch_bytes = 0;
+        VASR_CUDA_OK(cudaMalloc(&m->scratch, off));
+        m->scratch_bytes = off;
+    }
+    char* s = (char*)m->scratch;
+    VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave, wave_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    VASR_CUDA_OK(cudaMemcpyAsync(s + o_len, length_host, (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = vasr_frontend_forward(fe, (const float*)(s + o_wave), (const int64_t*)(s + o_len), B, L,
+                                    (float*)(s + o_feat), (int64_t*)(s + o_seq), st))) return rc;
+    if ((rc = vasr_encoder_forward(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
+                                   (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st))) return rc;
+    if ((rc = vasr_decoder_forward(m, (const float*)(s + o_enc), B, T_e, nullptr, (int64_t*)(s + o_ids), st))) return rc;
+    if ((rc = vasr_ctc_collapse((const int64_t*)(s + o_ids), B, T_e, m->num_classes - 1, (int32_t*)(s + o_oid),
+                                (int32_t*)(s + o_olen), st))) return rc;
+    VASR_CUDA_OK(cudaMemcpyAsync(out_ids_host, s + o_oid, (size_t)B * T_e * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VASR_CUDA_OK(cudaMemcpyAsync(out_len_host, s + o_olen, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VASR_CUDA_OK(cudaStreamSynchronize(st));
+    return VASR_OK;
+}

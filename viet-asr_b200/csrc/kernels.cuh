@@ -1,0 +1,30 @@
+// Internal launch wrappers shared between translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace vasr {
+
+int launch_lens(const long long* seq_len, int B, int n_stage, const int* st_k, const int* st_s,
+                const int* st_d, const int* st_p, int* lens, float* enc_len, cudaStream_t st);
+
+int launch_dw_conv(const float* x, const float* w, float* y, int B, int C, int T_in, int T_out,
+                   int K, int S, int D, int pad, const int* len_in, const int* len_out, cudaStream_t st);
+
+int launch_pw_gemm(const float* X, const float* W, int Cin, const float* R, const float* Wr, int Cres,
+                   const float* shift, float* Y, int B, int T, int Cout, const int* len, int relu,
+                   int mask_tail, cudaStream_t st);
+
+int launch_decoder(const float* enc, const float* W, const float* bias, int Cin, int V1,
+                   int N, float* logp, long long* ids, cudaStream_t st);
+
+int launch_ctc_collapse(const long long* ids, int B, int T, int blank, int* out_ids, int* out_len,
+                        cudaStream_t st);
+
+// tcgen05 fused sub-block (encoder_tc.cu); returns VASR_EINVAL when the shape is not built
+int launch_subblock_tc(const SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
+                       int T_out, const int* len_in, const int* len_out, int split3, cudaStream_t st);
+bool subblock_tc_supported(const SubBlock& sb);
+int tc_init();
+
+}  // namespace vasr

@@ -1,0 +1,116 @@
+"""Batched greedy-CTC inference engine: the data-parallel hot path end to end.
+
+`VietASR` keeps the reference class's constructor/`transcribe` contract
+(infer.py:57-171) but runs the greedy wiring (infer.py:113) on the GPU and
+accepts batches.  Two execution routes share the same kernels:
+
+  * `transcribe_batch_device` - module by module through the neural-module API
+    (device tensors in, device tensors out); used by parity tests and the
+    device-resident throughput measurement;
+  * `transcribe_host` - one C-ABI call `vasr_transcribe_host` with HOST buffers
+    (H2D of the waveforms and D2H of the collapsed ids inside the call); the
+    end-to-end number of bench.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, asr, configs
+from .nm import DeviceType, NeuralModuleFactory
+
+
+class VietASR:
+    def __init__(self, config_file: Optional[str] = None, encoder_checkpoint: Optional[str] = None,
+                 decoder_checkpoint: Optional[str] = None, device: str = "gpu", lm_path: Optional[str] = None,
+                 beam_width: int = 20, lm_alpha: float = 0.5, lm_beta: float = 1.5, *,
+                 model_definition: Optional[Dict] = None, gemm_mode: str = "fp32"):
+        if device != "gpu" or not torch.cuda.is_available():
+            raise RuntimeError("vasr_b200.VietASR runs on a CUDA device only (device='gpu'); there is no CPU path")
+        if lm_path is not None:
+            raise NotImplementedError("beam search + KenLM rescoring is not built yet (SURVEY.md section 8f.1); "
+                                      "pass lm_path=None for the greedy path")
+        if model_definition is None:
+            if config_file is None:
+                raise ValueError("either config_file or model_definition is required")
+            model_definition = configs.load_model_definition(config_file)
+        md = model_definition
+        pre = dict(md["AudioToMelSpectrogramPreprocessor"])
+        pre["dither"] = 0; pre["pad_to"] = 0                      # infer.py:89-90
+        if NeuralModuleFactory.get_default_factory() is None:
+            NeuralModuleFactory(placement=DeviceType.GPU)
+        self.labels: List[str] = list(md["labels"])
+        self.sample_rate = pre["sample_rate"]
+        self.preprocessor = asr.AudioToMelSpectrogramPreprocessor(**pre)
+        self.encoder = asr.JasperEncoder(feat_in=pre["features"], gemm_mode=gemm_mode, **md["JasperEncoder"])
+        self.decoder = asr.JasperDecoderForCTC(feat_in=md["JasperEncoder"]["jasper"][-1]["filters"],
+                                               num_classes=len(self.labels))
+        self.greedy = asr.GreedyCTCDecoder()
+        self.encoder.attach_decoder(self.decoder)
+        if encoder_checkpoint:
+            self.encoder.restore_from(encoder_checkpoint)
+        if decoder_checkpoint:
+            self.decoder.restore_from(decoder_checkpoint)
+
+    # ---- weights
+    def load_state_dicts(self, enc_sd, dec_sd):
+        self.encoder.load_state_dict(enc_sd)
+        self.decoder.load_state_dict(dec_sd)
+
+    def set_gemm_mode(self, mode: str):
+        self.encoder.set_gemm_mode(mode)
+
+    # ---- device route (module by module)
+    @torch.no_grad()
+    def forward_device(self, wave: torch.Tensor, length: torch.Tensor, want_log_probs: bool = False):
+        feat, seq = self.preprocessor.forward_channels_last(wave, length)
+        enc, enc_len = self.encoder.forward_channels_last(feat, seq)
+        logp, ids = self.decoder.forward_channels_last(enc, want_log_probs)
+        out_ids, out_len = asr.ctc_collapse(ids, len(self.labels))
+        return {"feat": feat, "seq": seq, "enc": enc, "enc_len": enc_len, "log_probs": logp, "ids": ids,
+                "out_ids": out_ids, "out_len": out_len}
+
+    def transcribe_batch_device(self, wave: torch.Tensor, length: torch.Tensor) -> List[str]:
+        r = self.forward_device(wave, length)
+        return asr.ids_to_text(r["out_ids"], r["out_len"], self.labels)
+
+    # ---- host route (one C-ABI call, host buffers)
+    def out_frames(self, L: int) -> int:
+        return self.encoder.out_frames(self.preprocessor.num_frames(L))
+
+    def transcribe_host_ids(self, wave_host: torch.Tensor, length_host: torch.Tensor,
+                            out_ids: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None):
+        """wave_host [B, L] f32 / length_host [B] i64 CPU tensors (pinned for async copies)."""
+        if wave_host.is_cuda or length_host.is_cuda:
+            raise ValueError("transcribe_host_ids takes host tensors")
+        w = wave_host.to(torch.float32).contiguous()
+        ln = length_host.to(torch.int64).contiguous()
+        B, L = w.shape
+        T_e = self.out_frames(L)
+        if out_ids is None:
+            out_ids = torch.empty((B, T_e), dtype=torch.int32).pin_memory()
+        if out_len is None:
+            out_len = torch.empty((B,), dtype=torch.int32).pin_memory()
+        h = self.encoder._sync_weights()
+        _lib.check(h.lib.vasr_transcribe_host(self.preprocessor._h, h.h, w.data_ptr(), ln.data_ptr(), B, L,
+                                              out_ids.data_ptr(), out_len.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+        return out_ids, out_len
+
+    def transcribe_batch(self, signals: Sequence[np.ndarray]) -> List[str]:
+        """List of 1-D float waveforms (16 kHz) -> transcripts; zero-pads to the longest
+        (the `seq_collate_fn` convention, parts/dataset.py:14-53)."""
+        lens = torch.tensor([len(s) for s in signals], dtype=torch.int64)
+        L = int(lens.max())
+        w = torch.zeros((len(signals), L), dtype=torch.float32)
+        for i, s in enumerate(signals):
+            w[i, : len(s)] = torch.as_tensor(np.asarray(s), dtype=torch.float32)
+        ids, n = self.transcribe_host_ids(w.pin_memory(), lens.pin_memory())
+        return asr.ids_to_text(ids, n, self.labels)
+
+    def transcribe(self, audio_signal: np.ndarray) -> str:
+        """infer.py:167-171: one utterance -> text."""
+        return self.transcribe_batch([np.reshape(audio_signal, [-1])])[0]
