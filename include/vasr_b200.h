@@ -62,8 +62,9 @@ typedef enum vasr_status {
 /* precision of the 1x1 (pointwise / residual / final) GEMMs of the encoder */
 typedef enum vasr_gemm_mode {
     VASR_GEMM_FP32_SIMT = 0,  /* fp32 FMA on CUDA cores (exact-order reference path)          */
-    VASR_GEMM_TF32X3    = 1,  /* tcgen05 kind::tf32, 3-term split: fp32-grade (parity mode)    */
-    VASR_GEMM_TF32X1    = 2   /* tcgen05 kind::tf32, single pass (fast mode, ~5e-4 rel logits) */
+    VASR_GEMM_F16X3     = 1,  /* tcgen05 kind::f16, fp16 hi/lo split on both operands, 3 products:
+                                 fp32-grade (parity mode)                                        */
+    VASR_GEMM_F16X1     = 2   /* tcgen05 kind::f16, single product (fast mode, ~5e-4 rel logits) */
 } vasr_gemm_mode;
 
 /* One Jasper block, fields as in the YAML `jasper:` list (jasper.py:27-66). */

@@ -34,7 +34,7 @@ def _engine(V, md, enc_sd, dec_sd, mode):
     return eng
 
 
-MODES = ["fp32", "tf32x3"]
+MODES = ["fp32", "f16x3"]
 
 
 # ----------------------------------------------------------------------------- front end

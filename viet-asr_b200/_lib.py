@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvasr_b200.so")
 
 VASR_OK, VASR_EINVAL, VASR_ECUDA, VASR_ESTATE, VASR_ENOMEM = 0, -1, -2, -3, -4
-GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32X1 = 0, 1, 2
-GEMM_MODES = {"fp32": GEMM_FP32_SIMT, "tf32x3": GEMM_TF32X3, "tf32x1": GEMM_TF32X1}
+GEMM_FP32_SIMT, GEMM_F16X3, GEMM_F16X1 = 0, 1, 2
+GEMM_MODES = {"fp32": GEMM_FP32_SIMT, "f16x3": GEMM_F16X3, "f16x1": GEMM_F16X1}
 
 
 class BlockCfg(C.Structure):

@@ -312,7 +312,7 @@ class JasperEncoder(TrainableNM):
                 nn.init.xavier_uniform_(p, gain=1.0)       # init_weights(mode='xavier_uniform'), parts/jasper.py:27-52
         self._gemm_mode = gemm_mode
         self._model: Optional[_ModelHandle] = None
-        self._decoder: Optional["JasperDecoderForCTC"] = None
+        self.__dict__["_decoder"] = None        # Optional[JasperDecoderForCTC], see attach_decoder
         self._dirty = True
         self._ws: Optional[torch.Tensor] = None
         if self._device.type != "cuda" or torch.cuda.is_available():
@@ -329,8 +329,10 @@ class JasperEncoder(TrainableNM):
         """Share one C handle (encoder + decoder head) - needed by the fused whole-path host call."""
         if decoder._feat_in != self._out_ch:
             raise ValueError(f"decoder feat_in {decoder._feat_in} != encoder output channels {self._out_ch}")
-        self._decoder = decoder
-        decoder._shared_from = self
+        # plain attribute slots: registering either module as a child of the other would make the
+        # nn.Module tree cyclic
+        self.__dict__["_decoder"] = decoder
+        decoder.__dict__["_shared_from"] = self
         self._model = None
         self._dirty = True
         decoder._dirty = True
@@ -406,7 +408,7 @@ class JasperDecoderForCTC(TrainableNM):
         self.decoder_layers = nn.Sequential(nn.Conv1d(feat_in, self._num_classes, kernel_size=1, bias=True))
         nn.init.xavier_uniform_(self.decoder_layers[0].weight, gain=1.0)
         self._own: Optional[_ModelHandle] = None      # decoder-only C handle (no encoder blocks)
-        self._shared_from: Optional[JasperEncoder] = None
+        self.__dict__["_shared_from"] = None     # Optional[JasperEncoder], see JasperEncoder.attach_decoder
         self._dirty = True
         if self._device.type != "cuda" or torch.cuda.is_available():
             self.to(self._device)      # jasper.py:196,251 (without a GPU only the symbolic graph can be built)

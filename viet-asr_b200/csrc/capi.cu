@@ -26,16 +26,6 @@ int set_error(int code, const char* fmt, ...)
 
 struct HostTensor { std::vector<int64_t> dims; std::vector<float> data; };
 
-static inline float round_tf32(float x)
-{
-    uint32_t u; memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return x;   // inf / nan
-    u += 0x1000u;                                      // round to nearest, ties away (cvt.rna.tf32.f32)
-    u &= 0xffffe000u;
-    float r; memcpy(&r, &u, 4);
-    return r;
-}
-
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace vasr
@@ -118,23 +108,14 @@ static int bn_fold(vasr_model* m, const std::string& prefix, int c, std::vector<
     return VASR_OK;
 }
 
-static int upload_gemm_weight(vasr_model* m, const HostTensor* w, const std::vector<float>& scale, int cout, int cin,
-                              float** d_w, float** d_hi, float** d_lo)
+// fold the BN scale into a [cout][cin] 1x1 weight (host) and upload the fp32 copy for the CUDA-core path
+static int fold_and_upload(vasr_model* m, const HostTensor* w, const std::vector<float>& scale, int cout, int cin,
+                           std::vector<float>& folded, float** d_w)
 {
-    std::vector<float> f((size_t)cout * cin), hi(f.size()), lo(f.size());
+    folded.resize((size_t)cout * cin);
     for (int o = 0; o < cout; ++o)
-        for (int i = 0; i < cin; ++i) {
-            const float v = w->data[(size_t)o * cin + i] * scale[o];
-            f[(size_t)o * cin + i] = v;
-            const float h = round_tf32(v);
-            hi[(size_t)o * cin + i] = h;
-            lo[(size_t)o * cin + i] = v - h;
-        }
-    int rc;
-    if ((rc = dev_upload(m, f, d_w))) return rc;
-    if ((rc = dev_upload(m, hi, d_hi))) return rc;
-    if ((rc = dev_upload(m, lo, d_lo))) return rc;
-    return VASR_OK;
+        for (int i = 0; i < cin; ++i) folded[(size_t)o * cin + i] = w->data[(size_t)o * cin + i] * scale[o];
+    return dev_upload(m, folded, d_w);
 }
 
 }  // namespace vasr
@@ -208,7 +189,7 @@ extern "C" int vasr_model_finalize(vasr_model* m, int gemm_mode)
 {
     using namespace vasr;
     VASR_REQUIRE(m, "vasr_model_finalize: null model");
-    VASR_REQUIRE(gemm_mode >= VASR_GEMM_FP32_SIMT && gemm_mode <= VASR_GEMM_TF32X1,
+    VASR_REQUIRE(gemm_mode >= VASR_GEMM_FP32_SIMT && gemm_mode <= VASR_GEMM_F16X1,
                  "vasr_model_finalize: unknown gemm_mode %d", gemm_mode);
     for (void* p : m->allocs) cudaFree(p);
     m->allocs.clear(); m->layers.clear();
@@ -252,15 +233,23 @@ extern "C" int vasr_model_finalize(vasr_model* m, int gemm_mode)
                 if ((rc = bn_fold(m, pre + std::to_string(per * r + 1), c.filters, scale, shift))) return rc;
             }
             sb.len_stage_out = stage;
-            if ((rc = upload_gemm_weight(m, w, scale, c.filters, ci, &sb.pw_w, &sb.pw_hi, &sb.pw_lo))) return rc;
+            std::vector<float> f_main, f_res;
+            if ((rc = fold_and_upload(m, w, scale, c.filters, ci, f_main, &sb.pw_w))) return rc;
             if (sb.has_res) {
                 const HostTensor* wr;
                 std::vector<float> rscale, rshift;
                 const std::string rp = "encoder." + std::to_string(b) + ".res.0.";
                 if ((rc = get_tensor(m, rp + "0.conv.weight", {c.filters, block_cin, 1}, &wr))) return rc;
                 if ((rc = bn_fold(m, rp + "1", c.filters, rscale, rshift))) return rc;
-                if ((rc = upload_gemm_weight(m, wr, rscale, c.filters, block_cin, &sb.res_w, &sb.res_hi, &sb.res_lo))) return rc;
+                if ((rc = fold_and_upload(m, wr, rscale, c.filters, block_cin, f_res, &sb.res_w))) return rc;
                 for (int i = 0; i < c.filters; ++i) shift[i] += rshift[i];
+            }
+            if (gemm_mode != VASR_GEMM_FP32_SIMT) {
+                if ((rc = tc_init())) return rc;
+                VASR_REQUIRE(subblock_tc_supported(sb),
+                             "tcgen05 path: sub-block (cin=%d cout=%d k=%d s=%d d=%d) is not a built shape",
+                             sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
+                if ((rc = tc_prepare_layer(sb, f_main.data(), sb.has_res ? f_res.data() : nullptr, m->allocs))) return rc;
             }
             if ((rc = dev_upload(m, shift, &sb.shift))) return rc;
             if (!sb.final_layer) cmax = std::max(cmax, sb.cout);
@@ -284,13 +273,6 @@ extern "C" int vasr_model_finalize(vasr_model* m, int gemm_mode)
         if ((rc = get_tensor(m, "decoder_layers.0.bias", {m->num_classes}, &db))) return rc;
         if ((rc = dev_upload(m, dw->data, &m->d_dec_w))) return rc;
         if ((rc = dev_upload(m, db->data, &m->d_dec_b))) return rc;
-    }
-    if (gemm_mode != VASR_GEMM_FP32_SIMT) {
-        if ((rc = tc_init())) return rc;
-        for (const SubBlock& sb : m->layers)
-            VASR_REQUIRE(subblock_tc_supported(sb),
-                         "tcgen05 path: sub-block (cin=%d cout=%d k=%d s=%d d=%d) is not a built shape",
-                         sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
     }
     m->gemm_mode = gemm_mode;
     m->finalized = true;
@@ -371,7 +353,7 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
             const float* res = sb.has_res ? block_in : nullptr;
             if (m->gemm_mode != VASR_GEMM_FP32_SIMT) {
                 if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
-                                             m->gemm_mode == VASR_GEMM_TF32X3, st))) return rc;
+                                             m->gemm_mode == VASR_GEMM_F16X3, st))) return rc;
             } else {
                 const float* gin = cur;
                 if (sb.separable) {

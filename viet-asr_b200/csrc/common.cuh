@@ -60,9 +60,15 @@ struct SubBlock {
     float* pw_w = nullptr;     // [cout][cin]     scale-folded, K-major
     float* res_w = nullptr;    // [cout][res_cin] scale-folded
     float* shift = nullptr;    // [cout]  (BN shift, + residual BN shift)
-    // tcgen05 operand copies (hi / lo split, tf32-rounded), same [cout][cin] layout
-    float* pw_hi = nullptr; float* pw_lo = nullptr;
-    float* res_hi = nullptr; float* res_lo = nullptr;
+    // tcgen05 operands: fp16 hi / lo split of the (power-of-two pre-scaled) weights, [cout][cin],
+    // the inverse pre-scale per output channel, and the TMA descriptors (CUtensorMap, 128 B each)
+    void* pw_h = nullptr; void* pw_l = nullptr;
+    void* res_h = nullptr; void* res_l = nullptr;
+    float* wscale_inv = nullptr;
+    alignas(64) unsigned char tm_w_hi[128];
+    alignas(64) unsigned char tm_w_lo[128];
+    alignas(64) unsigned char tm_r_hi[128];
+    alignas(64) unsigned char tm_r_lo[128];
 };
 
 }  // namespace vasr

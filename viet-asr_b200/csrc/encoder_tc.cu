@@ -1,9 +1,573 @@
-// tcgen05 fused sub-block (placeholder until the tensor path lands)
+// Fused QuartzNet sub-block for sm_100a:   depthwise conv (CUDA cores, register sliding window)
+//   -> fp16 hi/lo split written straight into the swizzled smem B operand
+//   -> 1x1 conv(s) on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   -> BN shift + residual (second GEMM chain into the same TMEM tile) + ReLU + length mask epilogue.
+// Restates one sub-block of JasperBlock.forward (nemo/collections/asr/parts/jasper.py:408-448) per launch.
+//
+// Tile: one utterance b, TN = 128 output time steps, up to 512 output channels
+//       D[co, t] (M = 128 co per MMA, N = 128 t) = W[co, ci] (A, K-major, TMA) x Act[t, ci] (B, K-major, written
+//       by the depthwise warps), chunked over ci in KC = 32 (64-byte fp16 rows -> SWIZZLE_64B).
+// Precision: fp16 operands with a 2-term split  x = hi + lo  on both sides and three products
+//       hi*hi + lo*hi + hi*lo  (fp32-grade, mode 1) or hi*hi only (mode 2).  Weights are pre-scaled per output
+//       channel by a power of two so that hi/lo stay in fp16's normal range; the scale is undone in the epilogue.
+// Warp roles (352 threads): 0..7 depthwise producers + epilogue, 8 = TMA producer of the activation window,
+//       9 = TMA producer of the weight slots, 10 = tcgen05.mma issuer (+ TMEM alloc/dealloc).
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <vector>
+#include <math.h>
+#include <string.h>
+
 namespace vasr {
-int tc_init() { return VASR_OK; }
-bool subblock_tc_supported(const SubBlock&) { return false; }
-int launch_subblock_tc(const SubBlock&, const float*, const float*, float*, int, int, int, const int*, const int*, int, cudaStream_t)
-{ return set_error(VASR_EINVAL, "tcgen05 path not built"); }
+namespace tc {
+
+constexpr int TN = 128;                 // output time steps per CTA
+constexpr int KC = 32;                  // input channels per chunk
+constexpr int NDW = 8;                  // depthwise / epilogue warps
+constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10;
+constexpr int NTHREADS = 11 * 32;
+constexpr int XSTAGES = 2, BSTAGES = 2;
+constexpr int PART_BYTES = 128 * KC * 2;   // one [128 rows x 64 B] fp16 operand tile = 8 KiB
+constexpr int MAX_CO_CTA = 512;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile [rows x 64 B], SWIZZLE_64B: 8-row groups of 512 B (SBO), canonical
+// ((8,n),2):((4,SBO),1) in 16-byte units (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::K>).
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address        bits [0,14)
+    d |= (uint64_t)1 << 16;                                  // leading byte offset  bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(512u >> 4) << 32;                        // stride byte offset   bits [32,46): 8 rows x 64 B
+    d |= (uint64_t)1 << 46;                                  // descriptor version 1 (sm_100)
+    d |= (uint64_t)4 << 61;                                  // layout type: SWIZZLE_64B
+    return d;
+}
+// byte offset of element (row, 16-byte chunk c16 in 0..3) inside a SWIZZLE_64B K-major tile
+__device__ __forceinline__ uint32_t sw64_offset(int row, int c16)
+{
+    return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((c16 ^ ((row >> 1) & 3)) << 4));
+}
+
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=128 (cute UMMA::InstrDescriptor)
+constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) |
+                                         ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Params {
+    const float* dw_w;       // [K][Cin] fp32 (ones for a plain 1x1 conv)
+    const float* shift;      // [Cout]
+    const float* wscale_inv; // [Cout] 2^-s of the weight pre-scale
+    float* out;              // [B, T_out, Cout]
+    const int* len_out;      // [B]
+    int Cin, Cres, Cout, T_out, pad;
+    int n_main, n_res;       // chunks of 32 input channels
+    int nM;                  // 128-row M blocks per CTA (2 or 4)
+    int n_xbox, xbox_rows, x_stage_bytes;
+    int relu, mask_tail, aslots;
+};
+
+template <int K, int S, int D, int NPART>
+__global__ void __launch_bounds__(NTHREADS, 1)
+subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_r,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
+                const Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve-up (every operand tile 1024-byte aligned; the launch reserves 1 KiB of slack for this round-up)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int A_SLOT = PART_BYTES * NPART, B_STAGE = PART_BYTES * NPART;
+    unsigned char* a_ring = smem;
+    unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
+    unsigned char* x_ring = b_ring + BSTAGES * B_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + XSTAGES * p.x_stage_bytes);
+    uint64_t* full_x = bars;                 // [XSTAGES]  TMA -> dw warps
+    uint64_t* empty_x = full_x + XSTAGES;    // [XSTAGES]  dw warps -> TMA
+    uint64_t* full_b = empty_x + XSTAGES;    // [BSTAGES]  dw warps -> MMA
+    uint64_t* empty_b = full_b + BSTAGES;    // [BSTAGES]  MMA (commit) -> dw warps
+    uint64_t* full_a = empty_b + BSTAGES;    // [aslots]   TMA -> MMA
+    uint64_t* empty_a = full_a + 16;         // [aslots]   MMA (commit) -> TMA
+    uint64_t* acc_full = empty_a + 16;       // [1]        MMA -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * TN;
+    const int co0 = blockIdx.y * (p.nM * 128);
+    const int b = blockIdx.z;
+    const int nchunks = p.n_main + p.n_res;
+    const uint32_t tmem_cols = (uint32_t)(p.nM * 128);     // 256 or 512: a power of two >= 32
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, NDW); }
+        for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, NDW); mbar_init(empty_b + i, 1); }
+        for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (warp == WARP_X && lane == 0) { tma_prefetch_desc(&tm_x); if (p.n_res) tma_prefetch_desc(&tm_r); }
+    if (warp == WARP_A && lane == 0) {
+        tma_prefetch_desc(&tm_w_hi);
+        if (NPART == 2) tma_prefetch_desc(&tm_w_lo);
+        if (p.n_res) { tma_prefetch_desc(&tm_r_hi); if (NPART == 2) tma_prefetch_desc(&tm_r_lo); }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == WARP_X) {
+        // ================= TMA producer: activation window (fp32, [rows x 32 ch], no swizzle) =================
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % XSTAGES;
+                mbar_wait(empty_x + s, ((c / XSTAGES) & 1) ^ 1);
+                unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
+                if (c < p.n_main) {
+                    mbar_arrive_expect_tx(full_x + s, (uint32_t)(p.n_xbox * p.xbox_rows * KC * 4));
+                    for (int j = 0; j < p.n_xbox; ++j)
+                        tma_load_3d(dst + (size_t)j * p.xbox_rows * KC * 4, &tm_x, c * KC,
+                                    t0 * S - p.pad + j * p.xbox_rows, b, full_x + s);
+                } else {
+                    mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
+                    tma_load_3d(dst, &tm_r, (c - p.n_main) * KC, t0, b, full_x + s);
+                }
+            }
+        }
+    } else if (warp == WARP_A) {
+        // ================= TMA producer: weight slots [128 co x 32 ci] fp16 hi (+ lo), SWIZZLE_64B =================
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                const bool res = c >= p.n_main;
+                const int ci0 = (res ? c - p.n_main : c) * KC;
+                for (int m = 0; m < p.nM; ++m) {
+                    mbar_wait(empty_a + slot, ph ^ 1);
+                    mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
+                    unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
+                    tma_load_2d(dst, res ? &tm_r_hi : &tm_w_hi, ci0, co0 + m * 128, full_a + slot);
+                    if (NPART == 2) tma_load_2d(dst + PART_BYTES, res ? &tm_r_lo : &tm_w_lo, ci0, co0 + m * 128, full_a + slot);
+                    if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ================= tcgen05.mma issuer (one thread) =================
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                const int sb = c % BSTAGES;
+                mbar_wait(full_b + sb, (c / BSTAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
+                for (int m = 0; m < p.nM; ++m) {
+                    mbar_wait(full_a + slot, ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
+                    const uint32_t d = tmem_base + (uint32_t)(m * 128);
+#pragma unroll
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint64_t a_hi = make_desc_sw64(a_addr + ks * 32);
+                        const uint64_t b_hi = make_desc_sw64(b_addr + ks * 32);
+                        umma_f16(d, a_hi, b_hi, IDESC_F16_M128_N128, (c > 0 || ks > 0) ? 1u : 0u);
+                        if (NPART == 2) {
+                            const uint64_t a_lo = make_desc_sw64(a_addr + PART_BYTES + ks * 32);
+                            const uint64_t b_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
+                            umma_f16(d, a_lo, b_hi, IDESC_F16_M128_N128, 1u);
+                            umma_f16(d, a_hi, b_lo, IDESC_F16_M128_N128, 1u);
+                        }
+                    }
+                    tcgen05_commit(empty_a + slot);        // weight slot reusable once these MMAs retire
+                    if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                }
+                tcgen05_commit(empty_b + sb);              // activation stage reusable
+            }
+            tcgen05_commit(acc_full);                      // accumulators complete
+        }
+    } else {
+        // ================= depthwise producers (warps 0..7): lane = channel within the chunk =================
+        constexpr int R = 16;                              // outputs per thread: t = t0 + 16*warp + r
+        const int tw = warp * R;
+        const int len_mid = p.len_out[b];    // the 1x1 conv masks its input rows t >= len (parts/jasper.py:116)
+        for (int c = 0; c < nchunks; ++c) {
+            const int sx = c % XSTAGES, sb = c % BSTAGES;
+            mbar_wait(full_x + sx, (c / XSTAGES) & 1);
+            const float* xs = reinterpret_cast<const float*>(x_ring + (size_t)sx * p.x_stage_bytes) + lane;
+            float acc[R];
+            if (c < p.n_main) {
+                const float* wp = p.dw_w + (size_t)c * KC + lane;
+                if (D == 1) {
+                    // window row of (output r, tap k) = (tw + r) * S + k
+                    constexpr int WIN = (R - 1) * S + K;
+                    float win[WIN];
+#pragma unroll
+                    for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw * S + j) * KC];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const float wk = __ldg(wp + (size_t)k * p.Cin);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = fmaf(wk, win[r * S + k], acc[r]);
+                    }
+                } else {
+                    // dilation 2 (stride 1): outputs of one parity share an every-other-row window
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        constexpr int RH = R / 2, WIN = RH - 1 + K;
+                        float win[WIN];
+#pragma unroll
+                        for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw + par + 2 * j) * KC];
+                        float a2[RH];
+#pragma unroll
+                        for (int r = 0; r < RH; ++r) a2[r] = 0.f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const float wk = __ldg(wp + (size_t)k * p.Cin);
+#pragma unroll
+                            for (int r = 0; r < RH; ++r) a2[r] = fmaf(wk, win[r + k], a2[r]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < RH; ++r) acc[2 * r + par] = a2[r];
+                    }
+                }
+            } else {
+                // residual branch: the block input itself (1x1 conv only)
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * KC];
+            }
+            // the depthwise output is not zero beyond len; the following MaskedConv1d zeroes it
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (t0 + tw + r >= len_mid) acc[r] = 0.f;
+
+            mbar_wait(empty_b + sb, ((c / BSTAGES) & 1) ^ 1);
+            unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
+            const int c16 = lane >> 3, e = lane & 7;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = tw + r;
+                const uint32_t off = sw64_offset(row, c16) + e * 2;
+                const __half h = __float2half_rn(acc[r]);
+                *reinterpret_cast<__half*>(bh + off) = h;
+                if (NPART == 2) {
+                    const __half l = __float2half_rn(acc[r] - __half2float(h));
+                    *reinterpret_cast<__half*>(bh + PART_BYTES + off) = l;
+                }
+            }
+            fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(full_b + sb); mbar_arrive(empty_x + sx); }
+        }
+
+        // ================= epilogue: TMEM -> registers -> +shift, ReLU, mask -> global (channels-last) =================
+        mbar_wait(acc_full, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const int len_o = p.len_out[b];
+        for (int m = 0; m < p.nM; ++m) {
+            const int co = co0 + m * 128 + q * 32 + lane;
+            const float sh = __ldg(p.shift + co), sc = __ldg(p.wscale_inv + co);
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                const int col0 = half * 64 + j * 32;
+                uint32_t rg[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 128 + col0), rg);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int t = t0 + col0 + i;
+                    if (t < p.T_out) {
+                        float v = fmaf(__uint_as_float(rg[i]), sc, sh);
+                        if (p.relu) v = fmaxf(v, 0.f);
+                        if (p.mask_tail && t >= len_o) v = 0.f;
+                        p.out[((size_t)b * p.T_out + t) * p.Cout + co] = v;
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int encode_tm(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                     const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw)
+{
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(tm, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VASR_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return VASR_OK;
+}
+
+// activations [B, T, C] fp32 -> 3-D map (C, T, B), box (32, rows, 1), no swizzle, zero OOB fill
+static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, int box_rows)
+{
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
+    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+// weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 128), SWIZZLE_64B
+static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)Cout};
+    cuuint64_t str[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 128};
+    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+struct KernelEntry { int K, S, D; const void* fn[2]; };
+#define TC_ENTRY(k, s, d) {k, s, d, {(const void*)subblock_kernel<k, s, d, 2>, (const void*)subblock_kernel<k, s, d, 1>}}
+static const KernelEntry g_kernels[] = {
+    TC_ENTRY(1, 1, 1), TC_ENTRY(33, 2, 1), TC_ENTRY(33, 1, 1), TC_ENTRY(39, 1, 1), TC_ENTRY(51, 1, 1),
+    TC_ENTRY(63, 1, 1), TC_ENTRY(75, 1, 1), TC_ENTRY(87, 1, 2), TC_ENTRY(11, 1, 1), TC_ENTRY(11, 2, 1), TC_ENTRY(15, 1, 2),
+};
+static const KernelEntry* find_kernel(int K, int S, int D)
+{
+    for (const KernelEntry& e : g_kernels)
+        if (e.K == K && e.S == S && e.D == D) return &e;
+    return nullptr;
+}
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* stage_bytes)
+{
+    const int rows = (TN - 1) * S + (K - 1) * D + 1;
+    int nb = (rows + 255) / 256, br = (rows + nb - 1) / nb;
+    br = (br + 7) / 8 * 8;
+    int bytes = nb * br * KC * 4;
+    if (bytes < TN * KC * 4) bytes = TN * KC * 4;            // residual / identity chunks load 128 rows
+    *n_xbox = nb; *xbox_rows = br; *stage_bytes = (bytes + 1023) / 1024 * 1024;
+}
+
+static int pick_aslots(int npart, int x_stage_bytes, int nM)
+{
+    const int fixed = BSTAGES * PART_BYTES * npart + XSTAGES * x_stage_bytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+    int slots = (SMEM_LIMIT - fixed) / (PART_BYTES * npart);
+    if (slots > 16) slots = 16;
+    if (slots > 2 * nM) slots = 2 * nM;                       // two chunks of look-ahead is plenty
+    return slots;
+}
+
+}  // namespace tc
+
+int tc_init()
+{
+    using namespace tc;
+    if (g_encode) return VASR_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VASR_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return set_error(VASR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    for (const KernelEntry& e : g_kernels)
+        for (int i = 0; i < 2; ++i)
+            VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    return VASR_OK;
+}
+
+bool subblock_tc_supported(const SubBlock& sb)
+{
+    using namespace tc;
+    const int K = sb.separable ? sb.kernel : 1;
+    if (!find_kernel(K, sb.stride, sb.dilation)) return false;
+    if (sb.cin % KC != 0 || (sb.has_res && sb.res_cin % KC != 0)) return false;
+    if (sb.cout % 256 != 0) return false;                      // nM in {2, 4} (TMEM columns a power of two)
+    if (sb.cout > MAX_CO_CTA && sb.cout % MAX_CO_CTA != 0) return false;
+    if (sb.has_res && sb.stride != 1) return false;
+    return true;
+}
+
+// weights: per-output-channel power-of-two pre-scale, fp16 hi/lo split, TMA maps
+int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, std::vector<void*>& allocs)
+{
+    using namespace tc;
+    const int Co = sb.cout, Ci = sb.cin, Cr = sb.has_res ? sb.res_cin : 0;
+    std::vector<float> inv(Co);
+    std::vector<__half> mh((size_t)Co * Ci), ml((size_t)Co * Ci), rh((size_t)Co * Cr), rl((size_t)Co * Cr);
+    for (int o = 0; o < Co; ++o) {
+        float mx = 0.f;
+        for (int i = 0; i < Ci; ++i) mx = fmaxf(mx, fabsf(w_main[(size_t)o * Ci + i]));
+        for (int i = 0; i < Cr; ++i) mx = fmaxf(mx, fabsf(w_res[(size_t)o * Cr + i]));
+        int ex = 0;
+        if (mx > 0.f && isfinite(mx)) frexpf(mx, &ex);          // mx = f * 2^ex, f in [0.5, 1)
+        const int s = (mx > 0.f) ? 14 - ex : 0;                   // scaled max in [2^13, 2^14)
+        const float sc = ldexpf(1.f, s);
+        inv[o] = ldexpf(1.f, -s);
+        auto split = [&](float v, __half& h, __half& l) {
+            const float x = v * sc;
+            h = __float2half_rn(x);
+            l = __float2half_rn(x - __half2float(h));
+        };
+        for (int i = 0; i < Ci; ++i) split(w_main[(size_t)o * Ci + i], mh[(size_t)o * Ci + i], ml[(size_t)o * Ci + i]);
+        for (int i = 0; i < Cr; ++i) split(w_res[(size_t)o * Cr + i], rh[(size_t)o * Cr + i], rl[(size_t)o * Cr + i]);
+    }
+    auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+        void* d = nullptr;
+        VASR_CUDA_OK(cudaMalloc(&d, bytes ? bytes : 16));
+        allocs.push_back(d);
+        if (bytes) VASR_CUDA_OK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        *dst = d;
+        return VASR_OK;
+    };
+    int rc;
+    if ((rc = up(inv.data(), sizeof(float) * Co, (void**)&sb.wscale_inv))) return rc;
+    if ((rc = up(mh.data(), sizeof(__half) * mh.size(), &sb.pw_h))) return rc;
+    if ((rc = up(ml.data(), sizeof(__half) * ml.size(), &sb.pw_l))) return rc;
+    static_assert(sizeof(CUtensorMap) == sizeof(sb.tm_w_hi), "tensor map storage");
+    if ((rc = encode_w((CUtensorMap*)sb.tm_w_hi, (const __half*)sb.pw_h, Co, Ci))) return rc;
+    if ((rc = encode_w((CUtensorMap*)sb.tm_w_lo, (const __half*)sb.pw_l, Co, Ci))) return rc;
+    if (Cr) {
+        if ((rc = up(rh.data(), sizeof(__half) * rh.size(), &sb.res_h))) return rc;
+        if ((rc = up(rl.data(), sizeof(__half) * rl.size(), &sb.res_l))) return rc;
+        if ((rc = encode_w((CUtensorMap*)sb.tm_r_hi, (const __half*)sb.res_h, Co, Cr))) return rc;
+        if ((rc = encode_w((CUtensorMap*)sb.tm_r_lo, (const __half*)sb.res_l, Co, Cr))) return rc;
+    } else {
+        memcpy(sb.tm_r_hi, sb.tm_w_hi, sizeof(sb.tm_w_hi));
+        memcpy(sb.tm_r_lo, sb.tm_w_lo, sizeof(sb.tm_w_lo));
+    }
+    if (!sb.separable) {
+        std::vector<float> ones(Ci, 1.0f);
+        if ((rc = up(ones.data(), sizeof(float) * Ci, (void**)&sb.dw_w))) return rc;
+    }
+    return VASR_OK;
+}
+
+int launch_subblock_tc(const SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
+                       int T_out, const int* len_in, const int* len_out, int split3, cudaStream_t st)
+{
+    using namespace tc;
+    (void)len_in;
+    const int K = sb.separable ? sb.kernel : 1;
+    const KernelEntry* ke = find_kernel(K, sb.stride, sb.dilation);
+    if (!ke || !subblock_tc_supported(sb))
+        return set_error(VASR_EINVAL, "tcgen05 path: sub-block (cin=%d cout=%d k=%d s=%d d=%d) is not a built shape",
+                         sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
+    const int npart = split3 ? 2 : 1;
+    Params p{};
+    p.dw_w = sb.dw_w; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv; p.out = y; p.len_out = len_out;
+    p.Cin = sb.cin; p.Cres = sb.has_res ? sb.res_cin : 0; p.Cout = sb.cout; p.T_out = T_out;
+    p.pad = sb.separable ? sb.pad : 0;
+    p.n_main = sb.cin / KC; p.n_res = sb.has_res ? sb.res_cin / KC : 0;
+    const int co_cta = sb.cout > MAX_CO_CTA ? MAX_CO_CTA : sb.cout;
+    p.nM = co_cta / 128;
+    x_geometry(K, sb.stride, sb.dilation, &p.n_xbox, &p.xbox_rows, &p.x_stage_bytes);
+    p.relu = sb.relu ? 1 : 0; p.mask_tail = sb.final_layer ? 0 : 1;
+    p.aslots = pick_aslots(npart, p.x_stage_bytes, p.nM);
+    if (p.aslots < 2) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
+    const size_t smem = (size_t)p.aslots * PART_BYTES * npart + (size_t)BSTAGES * PART_BYTES * npart +
+                        (size_t)XSTAGES * p.x_stage_bytes + 1024 + 1024;
+    CUtensorMap tm_x, tm_r;
+    int rc;
+    if ((rc = encode_act(&tm_x, x, B, T_in, sb.cin, p.xbox_rows))) return rc;
+    if (sb.has_res) { if ((rc = encode_act(&tm_r, res_in, B, T_in, sb.res_cin, TN))) return rc; }
+    else tm_r = tm_x;
+    dim3 grid(ceil_div(T_out, TN), sb.cout / co_cta, B);
+    void* args[] = {(void*)&tm_x, (void*)&tm_r, (void*)sb.tm_w_hi, (void*)sb.tm_w_lo, (void*)sb.tm_r_hi,
+                    (void*)sb.tm_r_lo, (void*)&p};
+    VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return VASR_OK;
+}
+
+}  // namespace vasr

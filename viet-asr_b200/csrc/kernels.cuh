@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "common.cuh"
+#include <vector>
 
 namespace vasr {
 
@@ -26,5 +27,7 @@ int launch_subblock_tc(const SubBlock& sb, const float* x, const float* res_in, 
                        int T_out, const int* len_in, const int* len_out, int split3, cudaStream_t st);
 bool subblock_tc_supported(const SubBlock& sb);
 int tc_init();
+// w_main [cout][cin], w_res [cout][res_cin] (or null): BN-scale-folded fp32 weights on the host
+int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, std::vector<void*>& allocs);
 
 }  // namespace vasr
