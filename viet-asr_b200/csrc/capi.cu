@@ -8,6 +8,7 @@
 #include <string>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace vasr {
 
@@ -43,6 +44,12 @@ struct vasr_model {
     float* d_dec_w = nullptr; float* d_dec_b = nullptr;
     int out_channels = 0;
     int cmax = 0;       // widest activation that lives in the workspace
+    // sub-batch streams of the tensor-core encoder path (tail of one sub-batch's layer overlaps the next layer
+    // of another: removes the wave-quantisation loss of 1 CTA/SM kernels)
+    std::vector<cudaStream_t> sub_streams;
+    std::vector<cudaEvent_t> sub_events;
+    cudaEvent_t fork_event = nullptr;
+    int max_sub = 4;
     // scratch of vasr_transcribe_host (grown on demand)
     void* scratch = nullptr; size_t scratch_bytes = 0;
 };
@@ -161,6 +168,9 @@ extern "C" void vasr_model_destroy(vasr_model* m)
     if (!m) return;
     for (void* p : m->allocs) cudaFree(p);
     if (m->scratch) cudaFree(m->scratch);
+    for (cudaStream_t s : m->sub_streams) cudaStreamDestroy(s);
+    for (cudaEvent_t e : m->sub_events) cudaEventDestroy(e);
+    if (m->fork_event) cudaEventDestroy(m->fork_event);
     delete m;
 }
 
@@ -214,13 +224,13 @@ extern "C" int vasr_model_finalize(vasr_model* m, int gemm_mode)
             sb.len_stage_in = stage;
             const std::string pre = "encoder." + std::to_string(b) + ".mconv.";
             const HostTensor* w;
-            std::vector<float> scale, shift;
+            std::vector<float> scale, shift, dwt;
             if (c.separable) {
                 const HostTensor* dw;
                 if ((rc = get_tensor(m, pre + std::to_string(per * r) + ".conv.weight", {ci, 1, c.kernel}, &dw))) return rc;
                 if ((rc = get_tensor(m, pre + std::to_string(per * r + 1) + ".conv.weight", {c.filters, ci, 1}, &w))) return rc;
                 if ((rc = bn_fold(m, pre + std::to_string(per * r + 2), c.filters, scale, shift))) return rc;
-                std::vector<float> dwt((size_t)c.kernel * ci);
+                dwt.resize((size_t)c.kernel * ci);
                 for (int ch = 0; ch < ci; ++ch)
                     for (int k = 0; k < c.kernel; ++k) dwt[(size_t)k * ci + ch] = dw->data[(size_t)ch * c.kernel + k];
                 if ((rc = dev_upload(m, dwt, &sb.dw_w))) return rc;
@@ -249,7 +259,8 @@ extern "C" int vasr_model_finalize(vasr_model* m, int gemm_mode)
                 VASR_REQUIRE(subblock_tc_supported(sb),
                              "tcgen05 path: sub-block (cin=%d cout=%d k=%d s=%d d=%d) is not a built shape",
                              sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
-                if ((rc = tc_prepare_layer(sb, f_main.data(), sb.has_res ? f_res.data() : nullptr, m->allocs))) return rc;
+                if ((rc = tc_prepare_layer(sb, f_main.data(), sb.has_res ? f_res.data() : nullptr,
+                                           c.separable ? dwt.data() : nullptr, m->allocs))) return rc;
             }
             if ((rc = dev_upload(m, shift, &sb.shift))) return rc;
             if (!sb.final_layer) cmax = std::max(cmax, sb.cout);
@@ -333,6 +344,30 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
     if ((rc = launch_lens((const long long*)seq_len, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
                           lens, enc_len, st))) return rc;
 
+    // ---- sub-batch plan: contiguous utterance ranges, each on its own stream (tensor path only)
+    const bool tc = m->gemm_mode != VASR_GEMM_FP32_SIMT;
+    int nsub = 1;
+    if (tc) {
+        const char* env = getenv("VASR_SUBSTREAMS");
+        int want = env ? atoi(env) : m->max_sub;
+        if (want < 1) want = 1;
+        if (want > 8) want = 8;
+        const int tiles_per_utt = ceil_div(vasr_model_out_frames(m, T_f), 128);
+        while (want > 1 && (B / want) * tiles_per_utt < 64) --want;     // keep every launch >= ~64 tiles
+        nsub = want;
+    }
+    if (nsub > 1) {
+        while ((int)m->sub_streams.size() < nsub) {
+            cudaStream_t s2; cudaEvent_t e2;
+            VASR_CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            VASR_CUDA_OK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            m->sub_streams.push_back(s2); m->sub_events.push_back(e2);
+        }
+        if (!m->fork_event) VASR_CUDA_OK(cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming));
+        VASR_CUDA_OK(cudaEventRecord(m->fork_event, st));
+        for (int s2 = 0; s2 < nsub; ++s2) VASR_CUDA_OK(cudaStreamWaitEvent(m->sub_streams[s2], m->fork_event, 0));
+    }
+
     const float* cur = feat;
     const float* block_in = feat;
     int T = T_f;
@@ -341,7 +376,7 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
         const vasr_block_cfg& c = m->blocks[b];
         block_in = cur;
         for (int r = 0; r < c.repeat; ++r, ++li) {
-            const SubBlock& sb = m->layers[li];
+            SubBlock& sb = m->layers[li];
             const int T_out = (T + 2 * sb.pad - sb.dilation * (sb.kernel - 1) - 1) / sb.stride + 1;
             float* out = nullptr;
             if (sb.final_layer) out = enc;
@@ -351,9 +386,14 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
             const int* len_in = lens + (size_t)sb.len_stage_in * B;
             const int* len_out = lens + (size_t)sb.len_stage_out * B;
             const float* res = sb.has_res ? block_in : nullptr;
-            if (m->gemm_mode != VASR_GEMM_FP32_SIMT) {
-                if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
-                                             m->gemm_mode == VASR_GEMM_F16X3, st))) return rc;
+            if (tc) {
+                for (int s2 = 0; s2 < nsub; ++s2) {
+                    const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
+                    if (b1 == b0) continue;
+                    if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
+                                                 m->gemm_mode == VASR_GEMM_F16X3, b0, b1 - b0,
+                                                 nsub > 1 ? m->sub_streams[s2] : st))) return rc;
+                }
             } else {
                 const float* gin = cur;
                 if (sb.separable) {
@@ -368,6 +408,11 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
             T = T_out;
         }
     }
+    if (nsub > 1)
+        for (int s2 = 0; s2 < nsub; ++s2) {
+            VASR_CUDA_OK(cudaEventRecord(m->sub_events[s2], m->sub_streams[s2]));
+            VASR_CUDA_OK(cudaStreamWaitEvent(st, m->sub_events[s2], 0));
+        }
     return VASR_OK;
 }
 

@@ -65,10 +65,15 @@ struct SubBlock {
     void* pw_h = nullptr; void* pw_l = nullptr;
     void* res_h = nullptr; void* res_l = nullptr;
     float* wscale_inv = nullptr;
+    float* dw_tc = nullptr;    // [cin/32][kernel][32] depthwise taps for the fused kernel
     alignas(64) unsigned char tm_w_hi[128];
     alignas(64) unsigned char tm_w_lo[128];
     alignas(64) unsigned char tm_r_hi[128];
     alignas(64) unsigned char tm_r_lo[128];
+    // cached activation tensor maps (whole batch) and the key they were encoded for
+    alignas(64) unsigned char tm_x[128];
+    alignas(64) unsigned char tm_r[128];
+    const void* tmc_x = nullptr; const void* tmc_r = nullptr; int tmc_B = 0, tmc_T = 0;
 };
 
 }  // namespace vasr

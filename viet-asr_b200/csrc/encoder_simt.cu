@@ -148,9 +148,10 @@ struct PwArgs {
     float* logp; long long* ids;
 };
 
+template <int TN>
 __device__ __forceinline__ void gemm_accumulate(const float* __restrict__ A, int lda, int a_rows, int row0,
                                                 const float* __restrict__ Bm, int ldb, int b_rows, int col0,
-                                                int Kdim, float (&acc)[8][8], float* As, float* Bs)
+                                                int Kdim, float (&acc)[8][TN], float* As, float* Bs)
 {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -162,7 +163,7 @@ __device__ __forceinline__ void gemm_accumulate(const float* __restrict__ A, int
             const int r = idx >> 2, kq = (idx & 3) * 4;
             float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
             if (row0 + r < a_rows) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)(row0 + r) * lda + k0 + kq));
-            if (col0 + r < b_rows) vb = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(col0 + r) * ldb + k0 + kq));
+            if (r < 16 * TN && col0 + r < b_rows) vb = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(col0 + r) * ldb + k0 + kq));
             As[(kq + 0) * GLD + r] = va.x; As[(kq + 1) * GLD + r] = va.y;
             As[(kq + 2) * GLD + r] = va.z; As[(kq + 3) * GLD + r] = va.w;
             Bs[(kq + 0) * GLD + r] = vb.x; Bs[(kq + 1) * GLD + r] = vb.y;
@@ -173,20 +174,25 @@ __device__ __forceinline__ void gemm_accumulate(const float* __restrict__ A, int
         for (int k = 0; k < GK; ++k) {
             const float4 a0 = *reinterpret_cast<const float4*>(As + k * GLD + ty * 8);
             const float4 a1 = *reinterpret_cast<const float4*>(As + k * GLD + ty * 8 + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * GLD + tx * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * GLD + tx * 8 + 4);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float bb[TN];
+#pragma unroll
+            for (int j = 0; j < TN; j += 2) {
+                const float2 bv = *reinterpret_cast<const float2*>(Bs + k * GLD + tx * TN + j);
+                bb[j] = bv.x; bb[j + 1] = bv.y;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
         __syncthreads();
     }
 }
 
-template <int EPI>
+// TN = output columns per thread: CTA tile = 128 rows x 16*TN columns (8 for the convs; the decoder picks the
+// smallest of {2, 4, 8} that covers its V+1 classes so a 29-class head does not pay for 128 columns)
+template <int EPI, int TN>
 __global__ void __launch_bounds__(256)
 pw_gemm_kernel(PwArgs p)
 {
@@ -195,17 +201,18 @@ pw_gemm_kernel(PwArgs p)
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int row0 = blockIdx.x * GM;      // rows n
-    const int col0 = blockIdx.y * GN;      // output channels
-    float acc[8][8];
+    const int col0 = blockIdx.y * (16 * TN);      // output channels
+    float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    gemm_accumulate(p.X, p.Cin, p.N, row0, p.W, p.Cin, p.Cout, col0, p.Cin, acc, As, Bs);
-    if (p.R) gemm_accumulate(p.R, p.Cres, p.N, row0, p.Wr, p.Cres, p.Cout, col0, p.Cres, acc, As, Bs);
+    gemm_accumulate<TN>(p.X, p.Cin, p.N, row0, p.W, p.Cin, p.Cout, col0, p.Cin, acc, As, Bs);
+    if (p.R) gemm_accumulate<TN>(p.R, p.Cres, p.N, row0, p.Wr, p.Cres, p.Cout, col0, p.Cres, acc, As, Bs);
 
-    if (EPI == EPI_CONV) {
+    if constexpr (EPI == EPI_CONV) {
+        static_assert(TN == 8, "conv epilogue is written for 8 columns per thread");
         float sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -239,38 +246,38 @@ pw_gemm_kernel(PwArgs p)
             }
         }
     } else {
-        // decoder: the whole class row (Cout <= 128) lives in the 16 lanes sharing `ty`
-        float bias[8];
+        // decoder: the whole class row (Cout <= 16*TN) lives in the 16 lanes sharing `ty`
+        float bias[TN];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int co = tx * 8 + j;
+        for (int j = 0; j < TN; ++j) {
+            const int co = tx * TN + j;
             bias[j] = (co < p.Cout) ? __ldg(p.shift + co) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int n = row0 + ty * 8 + i;
-            float v[8];
+            float v[TN];
             float mx = -FLT_MAX;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < TN; ++j) {
                 v[j] = acc[i][j] + bias[j];
-                if (tx * 8 + j < p.Cout) mx = fmaxf(mx, v[j]);
+                if (tx * TN + j < p.Cout) mx = fmaxf(mx, v[j]);
             }
 #pragma unroll
             for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float se = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (tx * 8 + j < p.Cout) se += expf(v[j] - mx);
+            for (int j = 0; j < TN; ++j)
+                if (tx * TN + j < p.Cout) se += expf(v[j] - mx);
 #pragma unroll
             for (int o = 8; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
             const float lse = logf(se);
             // greedy argmax over the log-probs, ties -> lowest index (torch.argmax)
             float best = -FLT_MAX; int bi = 0x7fffffff;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < TN; ++j) {
                 v[j] = (v[j] - mx) - lse;
-                const int co = tx * 8 + j;
+                const int co = tx * TN + j;
                 if (co < p.Cout && (v[j] > best)) { best = v[j]; bi = co; }
             }
 #pragma unroll
@@ -281,10 +288,10 @@ pw_gemm_kernel(PwArgs p)
             }
             if (n < p.N) {
                 if (p.logp) {
-                    float* lrow = p.logp + (size_t)n * p.Cout + tx * 8;
+                    float* lrow = p.logp + (size_t)n * p.Cout + tx * TN;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (tx * 8 + j < p.Cout) lrow[j] = v[j];
+                    for (int j = 0; j < TN; ++j)
+                        if (tx * TN + j < p.Cout) lrow[j] = v[j];
                 }
                 if (p.ids && tx == 0) p.ids[n] = (long long)bi;
             }
@@ -302,7 +309,7 @@ int launch_pw_gemm(const float* X, const float* W, int Cin, const float* R, cons
     p.X = X; p.W = W; p.Cin = Cin; p.R = R; p.Wr = Wr; p.Cres = Cres; p.shift = shift;
     p.Y = Y; p.N = B * T; p.Cout = Cout; p.T = T; p.len = len; p.relu = relu; p.mask_tail = mask_tail;
     dim3 grid(ceil_div(p.N, GM), ceil_div(Cout, GN));
-    pw_gemm_kernel<EPI_CONV><<<grid, 256, 0, st>>>(p);
+    pw_gemm_kernel<EPI_CONV, 8><<<grid, 256, 0, st>>>(p);
     VASR_LAUNCH_OK("pw_gemm_kernel<conv>");
     return VASR_OK;
 }
@@ -316,7 +323,9 @@ int launch_decoder(const float* enc, const float* W, const float* bias, int Cin,
     p.X = enc; p.W = W; p.Cin = Cin; p.shift = bias; p.N = N; p.Cout = V1; p.T = 1;
     p.logp = logp; p.ids = ids;
     dim3 grid(ceil_div(N, GM), 1);
-    pw_gemm_kernel<EPI_DECODER><<<grid, 256, 0, st>>>(p);
+    if (V1 <= 32) pw_gemm_kernel<EPI_DECODER, 2><<<grid, 256, 0, st>>>(p);
+    else if (V1 <= 64) pw_gemm_kernel<EPI_DECODER, 4><<<grid, 256, 0, st>>>(p);
+    else pw_gemm_kernel<EPI_DECODER, 8><<<grid, 256, 0, st>>>(p);
     VASR_LAUNCH_OK("pw_gemm_kernel<decoder>");
     return VASR_OK;
 }

@@ -142,7 +142,7 @@ constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | (0u << 7) | (0u << 10) | (0
                                          ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct Params {
-    const float* dw_w;       // [K][Cin] fp32 (ones for a plain 1x1 conv)
+    const float* dw_w;       // [Cin/32][K][32] fp32 depthwise taps (ones for a plain 1x1 conv)
     const float* shift;      // [Cout]
     const float* wscale_inv; // [Cout] 2^-s of the weight pre-scale
     float* out;              // [B, T_out, Cout]
@@ -152,6 +152,7 @@ struct Params {
     int nM;                  // 128-row M blocks per CTA (2 or 4)
     int n_xbox, xbox_rows, x_stage_bytes;
     int relu, mask_tail, aslots;
+    int b0;                  // first utterance of this launch (sub-batch on its own stream)
 };
 
 template <int K, int S, int D, int NPART>
@@ -181,7 +182,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = blockIdx.x * TN;
     const int co0 = blockIdx.y * (p.nM * 128);
-    const int b = blockIdx.z;
+    const int b = p.b0 + blockIdx.z;
     const int nchunks = p.n_main + p.n_res;
     const uint32_t tmem_cols = (uint32_t)(p.nM * 128);     // 256 or 512: a power of two >= 32
 
@@ -276,47 +277,62 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             tcgen05_commit(acc_full);                      // accumulators complete
         }
     } else {
-        // ================= depthwise producers (warps 0..7): lane = channel within the chunk =================
-        constexpr int R = 16;                              // outputs per thread: t = t0 + 16*warp + r
-        const int tw = warp * R;
+        // ================= depthwise producers (warps 0..7) =================
+        // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R = 8 outputs:
+        //   cp = lane & 15 -> channels 2cp, 2cp+1 of the chunk;  tg = 2*warp + (lane >> 4) -> t = 8*tg + r
+        constexpr int R = 8;
+        constexpr int NB = (K % 3 == 0 && K > 17) ? 3 : 1;     // taps are processed in NB register-window blocks
+        constexpr int KB = K / NB;
+        constexpr int XP = KC / 2;                               // float2 per window row
+        const int cp = lane & 15;
+        const int tw = (warp * 2 + (lane >> 4)) * R;
         const int len_mid = p.len_out[b];    // the 1x1 conv masks its input rows t >= len (parts/jasper.py:116)
         for (int c = 0; c < nchunks; ++c) {
             const int sx = c % XSTAGES, sb = c % BSTAGES;
             mbar_wait(full_x + sx, (c / XSTAGES) & 1);
-            const float* xs = reinterpret_cast<const float*>(x_ring + (size_t)sx * p.x_stage_bytes) + lane;
-            float acc[R];
+            const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
+            float2 acc[R];
             if (c < p.n_main) {
-                const float* wp = p.dw_w + (size_t)c * KC + lane;
+                // depthwise taps of this chunk, packed [chunk][K][32 ch] so every tap is a constant offset
+                const float2* wp = reinterpret_cast<const float2*>(p.dw_w + (size_t)c * K * KC) + cp;
+                constexpr int wstride = KC / 2;
                 if (D == 1) {
                     // window row of (output r, tap k) = (tw + r) * S + k
-                    constexpr int WIN = (R - 1) * S + K;
-                    float win[WIN];
 #pragma unroll
-                    for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw * S + j) * KC];
+                    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                    for (int kb = 0; kb < K; kb += KB) {
+                        constexpr int WIN = (R - 1) * S + KB;
+                        float2 win[WIN];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+                        for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw * S + kb + j) * XP];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float wk = __ldg(wp + (size_t)k * p.Cin);
+                        for (int kk = 0; kk < KB; ++kk) {
+                            const float2 wk = __ldg(wp + (size_t)(kb + kk) * wstride);
 #pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r] = fmaf(wk, win[r * S + k], acc[r]);
+                            for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[r * S + kk], acc[r]);
+                        }
                     }
                 } else {
                     // dilation 2 (stride 1): outputs of one parity share an every-other-row window
 #pragma unroll
                     for (int par = 0; par < 2; ++par) {
-                        constexpr int RH = R / 2, WIN = RH - 1 + K;
-                        float win[WIN];
+                        constexpr int RH = R / 2;
+                        float2 a2[RH];
 #pragma unroll
-                        for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw + par + 2 * j) * KC];
-                        float a2[RH];
+                        for (int r = 0; r < RH; ++r) a2[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                        for (int kb = 0; kb < K; kb += KB) {
+                            constexpr int WIN = RH - 1 + KB;
+                            float2 win[WIN];
 #pragma unroll
-                        for (int r = 0; r < RH; ++r) a2[r] = 0.f;
+                            for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw + par + 2 * (kb + j)) * XP];
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const float wk = __ldg(wp + (size_t)k * p.Cin);
+                            for (int kk = 0; kk < KB; ++kk) {
+                                const float2 wk = __ldg(wp + (size_t)(kb + kk) * wstride);
 #pragma unroll
-                            for (int r = 0; r < RH; ++r) a2[r] = fmaf(wk, win[r + k], a2[r]);
+                                for (int r = 0; r < RH; ++r) a2[r] = __ffma2_rn(wk, win[r + kk], a2[r]);
+                            }
                         }
 #pragma unroll
                         for (int r = 0; r < RH; ++r) acc[2 * r + par] = a2[r];
@@ -325,25 +341,24 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             } else {
                 // residual branch: the block input itself (1x1 conv only)
 #pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * KC];
+                for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
             }
             // the depthwise output is not zero beyond len; the following MaskedConv1d zeroes it
 #pragma unroll
             for (int r = 0; r < R; ++r)
-                if (t0 + tw + r >= len_mid) acc[r] = 0.f;
+                if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
 
             mbar_wait(empty_b + sb, ((c / BSTAGES) & 1) ^ 1);
             unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
-            const int c16 = lane >> 3, e = lane & 7;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int row = tw + r;
-                const uint32_t off = sw64_offset(row, c16) + e * 2;
-                const __half h = __float2half_rn(acc[r]);
-                *reinterpret_cast<__half*>(bh + off) = h;
+                const uint32_t off = sw64_offset(row, cp >> 2) + (cp & 3) * 4;
+                const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
+                *reinterpret_cast<__half2*>(bh + off) = h;
                 if (NPART == 2) {
-                    const __half l = __float2half_rn(acc[r] - __half2float(h));
-                    *reinterpret_cast<__half*>(bh + PART_BYTES + off) = l;
+                    const float2 hf = __half22float2(h);
+                    *reinterpret_cast<__half2*>(bh + PART_BYTES + off) = __floats2half2_rn(acc[r].x - hf.x, acc[r].y - hf.y);
                 }
             }
             fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -479,7 +494,8 @@ bool subblock_tc_supported(const SubBlock& sb)
 }
 
 // weights: per-output-channel power-of-two pre-scale, fp16 hi/lo split, TMA maps
-int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, std::vector<void*>& allocs)
+int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, const float* dw_kc,
+                     std::vector<void*>& allocs)
 {
     using namespace tc;
     const int Co = sb.cout, Ci = sb.cin, Cr = sb.has_res ? sb.res_cin : 0;
@@ -526,15 +542,20 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, std:
         memcpy(sb.tm_r_hi, sb.tm_w_hi, sizeof(sb.tm_w_hi));
         memcpy(sb.tm_r_lo, sb.tm_w_lo, sizeof(sb.tm_w_lo));
     }
-    if (!sb.separable) {
-        std::vector<float> ones(Ci, 1.0f);
-        if ((rc = up(ones.data(), sizeof(float) * Ci, (void**)&sb.dw_w))) return rc;
+    {   // depthwise taps re-packed per 32-channel chunk: [Cin/32][K][32]; identity for a plain 1x1 conv
+        const int K = sb.separable ? sb.kernel : 1;
+        std::vector<float> pk((size_t)Ci * K, 1.0f);
+        if (sb.separable)
+            for (int c = 0; c < Ci; ++c)
+                for (int k = 0; k < K; ++k)
+                    pk[((size_t)(c / KC) * K + k) * KC + (c % KC)] = dw_kc[(size_t)k * Ci + c];
+        if ((rc = up(pk.data(), sizeof(float) * pk.size(), (void**)&sb.dw_tc))) return rc;
     }
     return VASR_OK;
 }
 
-int launch_subblock_tc(const SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
-                       int T_out, const int* len_in, const int* len_out, int split3, cudaStream_t st)
+int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
+                       int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb, cudaStream_t st)
 {
     using namespace tc;
     (void)len_in;
@@ -545,7 +566,7 @@ int launch_subblock_tc(const SubBlock& sb, const float* x, const float* res_in, 
                          sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
     const int npart = split3 ? 2 : 1;
     Params p{};
-    p.dw_w = sb.dw_w; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv; p.out = y; p.len_out = len_out;
+    p.dw_w = sb.dw_tc; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv; p.out = y; p.len_out = len_out;
     p.Cin = sb.cin; p.Cres = sb.has_res ? sb.res_cin : 0; p.Cout = sb.cout; p.T_out = T_out;
     p.pad = sb.separable ? sb.pad : 0;
     p.n_main = sb.cin / KC; p.n_res = sb.has_res ? sb.res_cin / KC : 0;
@@ -557,14 +578,23 @@ int launch_subblock_tc(const SubBlock& sb, const float* x, const float* res_in, 
     if (p.aslots < 2) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
     const size_t smem = (size_t)p.aslots * PART_BYTES * npart + (size_t)BSTAGES * PART_BYTES * npart +
                         (size_t)XSTAGES * p.x_stage_bytes + 1024 + 1024;
-    CUtensorMap tm_x, tm_r;
+    p.b0 = b0;
+    // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
     int rc;
-    if ((rc = encode_act(&tm_x, x, B, T_in, sb.cin, p.xbox_rows))) return rc;
-    if (sb.has_res) { if ((rc = encode_act(&tm_r, res_in, B, T_in, sb.res_cin, TN))) return rc; }
-    else tm_r = tm_x;
-    dim3 grid(ceil_div(T_out, TN), sb.cout / co_cta, B);
-    void* args[] = {(void*)&tm_x, (void*)&tm_r, (void*)sb.tm_w_hi, (void*)sb.tm_w_lo, (void*)sb.tm_r_hi,
-                    (void*)sb.tm_r_lo, (void*)&p};
+    if (sb.tmc_x != x || sb.tmc_B != B || sb.tmc_T != T_in) {
+        if ((rc = encode_act((CUtensorMap*)sb.tm_x, x, B, T_in, sb.cin, p.xbox_rows))) return rc;
+        sb.tmc_x = x; sb.tmc_B = B; sb.tmc_T = T_in;
+        sb.tmc_r = nullptr;
+    }
+    if (sb.has_res) {
+        if (sb.tmc_r != res_in) {
+            if ((rc = encode_act((CUtensorMap*)sb.tm_r, res_in, B, T_in, sb.res_cin, TN))) return rc;
+            sb.tmc_r = res_in;
+        }
+    }
+    dim3 grid(ceil_div(T_out, TN), sb.cout / co_cta, nb);
+    void* args[] = {(void*)sb.tm_x, (void*)(sb.has_res ? sb.tm_r : sb.tm_x), (void*)sb.tm_w_hi, (void*)sb.tm_w_lo,
+                    (void*)sb.tm_r_hi, (void*)sb.tm_r_lo, (void*)&p};
     VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return VASR_OK;
