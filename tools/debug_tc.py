@@ -73,7 +73,7 @@ if __name__ == "__main__":
     for mode in ("f16x3", "f16x1"):
         for n in names:
             try:
-                p = subprocess.run([sys.executable, __file__, "--one", n, mode], capture_output=True, text=True, timeout=120)
+                p = subprocess.run([sys.executable, __file__, "--one", n, mode], capture_output=True, text=True, timeout=45)
                 lines = [l for l in p.stdout.splitlines() if l.startswith("DBG ")]
                 print(lines[-1] if lines else f"DBG {{\"case\": \"{n}\", \"mode\": \"{mode}\", \"rc\": {p.returncode}, \"err\": {json.dumps(p.stderr[-600:])}}}")
             except subprocess.TimeoutExpired:

@@ -28,6 +28,7 @@ int set_error(int code, const char* fmt, ...)
 struct HostTensor { std::vector<int64_t> dims; std::vector<float> data; };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t TILE_COUNTER_BYTES = 8192;   // one int per (layer, sub-batch) launch of the persistent kernels
 
 }  // namespace vasr
 
@@ -318,7 +319,7 @@ extern "C" size_t vasr_encoder_workspace_bytes(const vasr_model* m, int B, int T
     // (T never grows along the stack), + the length table
     const size_t act = vasr::align_up((size_t)B * T_f * m->cmax * sizeof(float), 256);
     const size_t lens = vasr::align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
-    return lens + 4 * act;
+    return lens + vasr::TILE_COUNTER_BYTES + 4 * act;
 }
 
 extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
@@ -336,11 +337,14 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     int* lens = (int*)ws;
-    const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
+    const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256) + TILE_COUNTER_BYTES;
+    int* counters = (int*)(ws + lens_b - TILE_COUNTER_BYTES);
     const size_t act = align_up((size_t)B * T_f * m->cmax * sizeof(float), 256);
     float* P[3] = {(float*)(ws + lens_b), (float*)(ws + lens_b + act), (float*)(ws + lens_b + 2 * act)};
     float* DW = (float*)(ws + lens_b + 3 * act);
     int rc;
+    VASR_REQUIRE(m->layers.size() * 8 * sizeof(int) <= TILE_COUNTER_BYTES, "too many layers for the tile-counter table");
+    if (m->gemm_mode != VASR_GEMM_FP32_SIMT) VASR_CUDA_OK(cudaMemsetAsync(counters, 0, TILE_COUNTER_BYTES, st));
     if ((rc = launch_lens((const long long*)seq_len, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
                           lens, enc_len, st))) return rc;
 
@@ -392,6 +396,7 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
                     if (b1 == b0) continue;
                     if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
                                                  m->gemm_mode == VASR_GEMM_F16X3, b0, b1 - b0,
+                                                 counters + li * 8 + s2,
                                                  nsub > 1 ? m->sub_streams[s2] : st))) return rc;
                 }
             } else {

@@ -25,10 +25,13 @@ namespace tc {
 
 constexpr int TN = 128;                 // output time steps per CTA
 constexpr int KC = 32;                  // input channels per chunk
-constexpr int NDW = 8;                  // depthwise / epilogue warps
-constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10;
-constexpr int NTHREADS = 11 * 32;
-constexpr int XSTAGES = 2, BSTAGES = 2;
+constexpr int NDW = 8;                  // depthwise warps 0..7
+constexpr int NEPI = 4;                 // epilogue warps 11..14: warp & 3 = 3,0,1,2 -> each TMEM lane quarter once
+constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10, WARP_EPI = 11;
+constexpr int NTHREADS = 15 * 32;
+constexpr int MAX_STAGES = 4;           // upper bound of the activation-window / B-operand ring depths
+constexpr int SCHED = 4;                // depth of the tile ring
+constexpr int SCHED_CONSUMERS = 1 /*A*/ + 1 /*MMA*/ + NDW + NEPI;
 constexpr int PART_BYTES = 128 * KC * 2;   // one [128 rows x 64 B] fp16 operand tile = 8 KiB
 constexpr int MAX_CO_CTA = 512;
 
@@ -36,6 +39,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +88,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// plain (non-tensor) bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
 {
@@ -147,14 +157,20 @@ struct Params {
     const float* wscale_inv; // [Cout] 2^-s of the weight pre-scale
     float* out;              // [B, T_out, Cout]
     const int* len_out;      // [B]
+    int* tile_counter;       // dynamic tile scheduler (zeroed before the launch)
     int Cin, Cres, Cout, T_out, pad;
     int n_main, n_res;       // chunks of 32 input channels
-    int nM;                  // 128-row M blocks per CTA (2 or 4)
-    int n_xbox, xbox_rows, x_stage_bytes;
+    int nM;                  // 128-row M blocks per tile (2 or 4)
+    int n_xbox, xbox_rows, x_stage_bytes, x_w_off;   // x_w_off: offset of the chunk's depthwise taps in a stage
+    int xstages, bstages;
     int relu, mask_tail, aslots;
     int b0;                  // first utterance of this launch (sub-batch on its own stream)
+    int n_tt, n_utt, n_cg;   // tiles: time tiles per utterance x utterances x output-channel groups
 };
 
+// Persistent CTA (one per SM): tiles are claimed from an atomic counter by the scheduler thread and published
+// to the other roles through a small shared-memory ring; all operand rings and the TMEM accumulator buffers
+// keep running across tiles, so the epilogue of tile i overlaps the depthwise/MMA work of tile i+1.
 template <int K, int S, int D, int NPART>
 __global__ void __launch_bounds__(NTHREADS, 1)
 subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_r,
@@ -168,33 +184,38 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     constexpr int A_SLOT = PART_BYTES * NPART, B_STAGE = PART_BYTES * NPART;
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
-    unsigned char* x_ring = b_ring + BSTAGES * B_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + XSTAGES * p.x_stage_bytes);
-    uint64_t* full_x = bars;                 // [XSTAGES]  TMA -> dw warps
-    uint64_t* empty_x = full_x + XSTAGES;    // [XSTAGES]  dw warps -> TMA
-    uint64_t* full_b = empty_x + XSTAGES;    // [BSTAGES]  dw warps -> MMA
-    uint64_t* empty_b = full_b + BSTAGES;    // [BSTAGES]  MMA (commit) -> dw warps
-    uint64_t* full_a = empty_b + BSTAGES;    // [aslots]   TMA -> MMA
+    unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + (size_t)p.xstages * p.x_stage_bytes);
+    const int XSTAGES = p.xstages, BSTAGES = p.bstages;
+    uint64_t* full_x = bars;                 // [xstages]  TMA -> dw warps
+    uint64_t* empty_x = full_x + MAX_STAGES; // [xstages]  dw warps -> TMA
+    uint64_t* full_b = empty_x + MAX_STAGES; // [bstages]  dw warps -> MMA
+    uint64_t* empty_b = full_b + MAX_STAGES; // [bstages]  MMA (commit) -> dw warps
+    uint64_t* full_a = empty_b + MAX_STAGES; // [aslots]   TMA -> MMA
     uint64_t* empty_a = full_a + 16;         // [aslots]   MMA (commit) -> TMA
-    uint64_t* acc_full = empty_a + 16;       // [1]        MMA -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* acc_full = empty_a + 16;       // [2]        MMA (commit) -> epilogue
+    uint64_t* acc_empty = acc_full + 2;      // [2]        epilogue -> MMA
+    uint64_t* sched_full = acc_empty + 2;    // [SCHED]    scheduler -> roles
+    uint64_t* sched_empty = sched_full + SCHED;  // [SCHED] roles -> scheduler
+    int* tile_ring = reinterpret_cast<int*>(sched_empty + SCHED);   // [SCHED]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + SCHED);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * TN;
-    const int co0 = blockIdx.y * (p.nM * 128);
-    const int b = p.b0 + blockIdx.z;
     const int nchunks = p.n_main + p.n_res;
-    const uint32_t tmem_cols = (uint32_t)(p.nM * 128);     // 256 or 512: a power of two >= 32
+    const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
+    const int acc_cols = p.nM * 128;                       // TMEM columns of one accumulator buffer
+    const int nbuf = (acc_cols <= 256) ? 2 : 1;            // double-buffered when it fits the 512 columns
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, NDW); }
         for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, NDW); mbar_init(empty_b + i, 1); }
         for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, NEPI); }
+        for (int i = 0; i < SCHED; ++i) { mbar_init(sched_full + i, 1); mbar_init(sched_empty + i, SCHED_CONSUMERS); }
         fence_barrier_init();
     }
     if (warp == WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (warp == WARP_X && lane == 0) { tma_prefetch_desc(&tm_x); if (p.n_res) tma_prefetch_desc(&tm_r); }
@@ -208,76 +229,161 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile id -> (output-channel group, utterance, time tile)
+    auto decode = [&](int tile, int& co0, int& b, int& t0) {
+        const int tt = tile % p.n_tt;
+        const int r = tile / p.n_tt;
+        b = p.b0 + r % p.n_utt;
+        co0 = (r / p.n_utt) * (p.nM * 128);
+        t0 = tt * TN;
+    };
+    // consumer side of the tile ring: returns the tile id (or -1 = no more work)
+    auto next_tile = [&](int ti) -> int {
+        const int slot = ti % SCHED;
+        mbar_wait(sched_full + slot, (ti / SCHED) & 1);
+        const int tile = tile_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sched_empty + slot);
+        return tile;
+    };
+
     if (warp == WARP_X) {
-        // ================= TMA producer: activation window (fp32, [rows x 32 ch], no swizzle) =================
+        // ======== scheduler + TMA producer of the activation window (fp32, [rows x 32 ch], no swizzle) ========
         if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % XSTAGES;
-                mbar_wait(empty_x + s, ((c / XSTAGES) & 1) ^ 1);
-                unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
-                if (c < p.n_main) {
-                    mbar_arrive_expect_tx(full_x + s, (uint32_t)(p.n_xbox * p.xbox_rows * KC * 4));
-                    for (int j = 0; j < p.n_xbox; ++j)
-                        tma_load_3d(dst + (size_t)j * p.xbox_rows * KC * 4, &tm_x, c * KC,
-                                    t0 * S - p.pad + j * p.xbox_rows, b, full_x + s);
-                } else {
-                    mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
-                    tma_load_3d(dst, &tm_r, (c - p.n_main) * KC, t0, b, full_x + s);
+            int gc = 0;
+            for (int ti = 0;; ++ti) {
+                const int slot = ti % SCHED;
+                mbar_wait(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
+                int tile = atomicAdd(p.tile_counter, 1);
+                if (tile >= n_tiles) tile = -1;
+                tile_ring[slot] = tile;
+                mbar_arrive(sched_full + slot);
+                if (tile < 0) break;
+                int co0, b, t0;
+                decode(tile, co0, b, t0);
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int s = gc % XSTAGES;
+                    mbar_wait(empty_x + s, ((gc / XSTAGES) & 1) ^ 1);
+                    unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
+                    if (c < p.n_main) {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(p.n_xbox * p.xbox_rows * KC * 4 + K * KC * 4));
+                        for (int j = 0; j < p.n_xbox; ++j)
+                            tma_load_3d(dst + (size_t)j * p.xbox_rows * KC * 4, &tm_x, c * KC,
+                                        t0 * S - p.pad + j * p.xbox_rows, b, full_x + s);
+                        // the chunk's depthwise taps [K][32] ride in the same stage (no exposed global-load latency)
+                        bulk_load(dst + p.x_w_off, p.dw_w + (size_t)c * K * KC, (uint32_t)(K * KC * 4), full_x + s);
+                    } else {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
+                        tma_load_3d(dst, &tm_r, (c - p.n_main) * KC, t0, b, full_x + s);
+                    }
                 }
             }
         }
     } else if (warp == WARP_A) {
-        // ================= TMA producer: weight slots [128 co x 32 ci] fp16 hi (+ lo), SWIZZLE_64B =================
-        if (lane == 0) {
-            int slot = 0; uint32_t ph = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                const bool res = c >= p.n_main;
-                const int ci0 = (res ? c - p.n_main : c) * KC;
-                for (int m = 0; m < p.nM; ++m) {
-                    mbar_wait(empty_a + slot, ph ^ 1);
-                    mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
-                    unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
-                    tma_load_2d(dst, res ? &tm_r_hi : &tm_w_hi, ci0, co0 + m * 128, full_a + slot);
-                    if (NPART == 2) tma_load_2d(dst + PART_BYTES, res ? &tm_r_lo : &tm_w_lo, ci0, co0 + m * 128, full_a + slot);
-                    if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+        // ======== TMA producer: weight slots [128 co x 32 ci] fp16 hi (+ lo), SWIZZLE_64B ========
+        int slot = 0; uint32_t ph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int co0, b, t0;
+            decode(tile, co0, b, t0);
+            if (lane == 0) {
+                for (int c = 0; c < nchunks; ++c) {
+                    const bool res = c >= p.n_main;
+                    const int ci0 = (res ? c - p.n_main : c) * KC;
+                    for (int m = 0; m < p.nM; ++m) {
+                        mbar_wait(empty_a + slot, ph ^ 1);
+                        mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
+                        unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
+                        tma_load_2d(dst, res ? &tm_r_hi : &tm_w_hi, ci0, co0 + m * 128, full_a + slot);
+                        if (NPART == 2) tma_load_2d(dst + PART_BYTES, res ? &tm_r_lo : &tm_w_lo, ci0, co0 + m * 128, full_a + slot);
+                        if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                    }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == WARP_MMA) {
-        // ================= tcgen05.mma issuer (one thread) =================
-        if (lane == 0) {
-            int slot = 0; uint32_t ph = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                const int sb = c % BSTAGES;
-                mbar_wait(full_b + sb, (c / BSTAGES) & 1);
+        // ======== tcgen05.mma issuer (one thread) ========
+        int slot = 0; uint32_t ph = 0;
+        int gc = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            if (lane == 0) {
+                const int ab = ti % nbuf;
+                mbar_wait(acc_empty + ab, ((ti / nbuf) & 1) ^ 1);     // epilogue has drained this accumulator buffer
                 tcgen05_fence_after();
-                const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
-                for (int m = 0; m < p.nM; ++m) {
-                    mbar_wait(full_a + slot, ph);
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int sb = gc % BSTAGES;
+                    mbar_wait(full_b + sb, (gc / BSTAGES) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
-                    const uint32_t d = tmem_base + (uint32_t)(m * 128);
+                    const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
+                    for (int m = 0; m < p.nM; ++m) {
+                        mbar_wait(full_a + slot, ph);
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
+                        const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 128);
 #pragma unroll
-                    for (int ks = 0; ks < KC / 16; ++ks) {
-                        const uint64_t a_hi = make_desc_sw64(a_addr + ks * 32);
-                        const uint64_t b_hi = make_desc_sw64(b_addr + ks * 32);
-                        umma_f16(d, a_hi, b_hi, IDESC_F16_M128_N128, (c > 0 || ks > 0) ? 1u : 0u);
-                        if (NPART == 2) {
-                            const uint64_t a_lo = make_desc_sw64(a_addr + PART_BYTES + ks * 32);
-                            const uint64_t b_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
-                            umma_f16(d, a_lo, b_hi, IDESC_F16_M128_N128, 1u);
-                            umma_f16(d, a_hi, b_lo, IDESC_F16_M128_N128, 1u);
+                        for (int ks = 0; ks < KC / 16; ++ks) {
+                            const uint64_t a_hi = make_desc_sw64(a_addr + ks * 32);
+                            const uint64_t b_hi = make_desc_sw64(b_addr + ks * 32);
+                            umma_f16(d, a_hi, b_hi, IDESC_F16_M128_N128, (c > 0 || ks > 0) ? 1u : 0u);
+                            if (NPART == 2) {
+                                const uint64_t a_lo = make_desc_sw64(a_addr + PART_BYTES + ks * 32);
+                                const uint64_t b_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
+                                umma_f16(d, a_lo, b_hi, IDESC_F16_M128_N128, 1u);
+                                umma_f16(d, a_hi, b_lo, IDESC_F16_M128_N128, 1u);
+                            }
+                        }
+                        tcgen05_commit(empty_a + slot);        // weight slot reusable once these MMAs retire
+                        if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                    }
+                    tcgen05_commit(empty_b + sb);              // activation stage reusable
+                }
+                tcgen05_commit(acc_full + ab);                 // accumulators of this tile complete
+            }
+            __syncwarp();
+        }
+    } else if (warp >= WARP_EPI) {
+        // ======== epilogue (4 warps): TMEM -> registers -> +shift, ReLU, mask -> global (channels-last) ========
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int co0, b, t0;
+            decode(tile, co0, b, t0);
+            const int ab = ti % nbuf;
+            const int len_o = p.len_out[b];
+            mbar_wait(acc_full + ab, (ti / nbuf) & 1);
+            tcgen05_fence_after();
+            for (int m = 0; m < p.nM; ++m) {
+                const int co = co0 + m * 128 + q * 32 + lane;
+                const float sh = __ldg(p.shift + co), sc = __ldg(p.wscale_inv + co);
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const int col0 = j * 32;
+                    uint32_t rg[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + m * 128 + col0), rg);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int t = t0 + col0 + i;
+                        if (t < p.T_out) {
+                            float v = fmaf(__uint_as_float(rg[i]), sc, sh);
+                            if (p.relu) v = fmaxf(v, 0.f);
+                            if (p.mask_tail && t >= len_o) v = 0.f;
+                            p.out[((size_t)b * p.T_out + t) * p.Cout + co] = v;
                         }
                     }
-                    tcgen05_commit(empty_a + slot);        // weight slot reusable once these MMAs retire
-                    if (++slot == p.aslots) { slot = 0; ph ^= 1; }
                 }
-                tcgen05_commit(empty_b + sb);              // activation stage reusable
             }
-            tcgen05_commit(acc_full);                      // accumulators complete
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + ab);        // accumulator buffer may be overwritten
         }
-    } else {
-        // ================= depthwise producers (warps 0..7) =================
+    } else if (warp < NDW) {
+        // ======== depthwise producers (warps 0..7) ========
         // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R = 8 outputs:
         //   cp = lane & 15 -> channels 2cp, 2cp+1 of the chunk;  tg = 2*warp + (lane >> 4) -> t = 8*tg + r
         constexpr int R = 8;
@@ -286,110 +392,90 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         constexpr int XP = KC / 2;                               // float2 per window row
         const int cp = lane & 15;
         const int tw = (warp * 2 + (lane >> 4)) * R;
-        const int len_mid = p.len_out[b];    // the 1x1 conv masks its input rows t >= len (parts/jasper.py:116)
-        for (int c = 0; c < nchunks; ++c) {
-            const int sx = c % XSTAGES, sb = c % BSTAGES;
-            mbar_wait(full_x + sx, (c / XSTAGES) & 1);
-            const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
-            float2 acc[R];
-            if (c < p.n_main) {
-                // depthwise taps of this chunk, packed [chunk][K][32 ch] so every tap is a constant offset
-                const float2* wp = reinterpret_cast<const float2*>(p.dw_w + (size_t)c * K * KC) + cp;
-                constexpr int wstride = KC / 2;
-                if (D == 1) {
-                    // window row of (output r, tap k) = (tw + r) * S + k
+        int gc = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int co0, b, t0;
+            decode(tile, co0, b, t0);
+            const int len_mid = p.len_out[b];    // the 1x1 conv masks its input rows t >= len (parts/jasper.py:116)
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const int sx = gc % XSTAGES, sb = gc % BSTAGES;
+                mbar_wait(full_x + sx, (gc / XSTAGES) & 1);
+                const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
+                float2 acc[R];
+                if (c < p.n_main) {
+                    // depthwise taps of this chunk [K][32 ch], staged in shared memory next to the window
+                    const float2* wp = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes + p.x_w_off) + cp;
+                    constexpr int wstride = KC / 2;
+                    if (D == 1) {
+                        // window row of (output r, tap k) = (tw + r) * S + k
 #pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+                        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
 #pragma unroll 1
-                    for (int kb = 0; kb < K; kb += KB) {
-                        constexpr int WIN = (R - 1) * S + KB;
-                        float2 win[WIN];
+                        for (int kb = 0; kb < K; kb += KB) {
+                            constexpr int WIN = (R - 1) * S + KB;
+                            float2 win[WIN];
 #pragma unroll
-                        for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw * S + kb + j) * XP];
+                            for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw * S + kb + j) * XP];
 #pragma unroll
-                        for (int kk = 0; kk < KB; ++kk) {
-                            const float2 wk = __ldg(wp + (size_t)(kb + kk) * wstride);
+                            for (int kk = 0; kk < KB; ++kk) {
+                                const float2 wk = wp[(size_t)(kb + kk) * wstride];
 #pragma unroll
-                            for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[r * S + kk], acc[r]);
+                                for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[r * S + kk], acc[r]);
+                            }
+                        }
+                    } else {
+                        // dilation 2 (stride 1): outputs of one parity share an every-other-row window
+#pragma unroll
+                        for (int par = 0; par < 2; ++par) {
+                            constexpr int RH = R / 2;
+                            float2 a2[RH];
+#pragma unroll
+                            for (int r = 0; r < RH; ++r) a2[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                            for (int kb = 0; kb < K; kb += KB) {
+                                constexpr int WIN = RH - 1 + KB;
+                                float2 win[WIN];
+#pragma unroll
+                                for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw + par + 2 * (kb + j)) * XP];
+#pragma unroll
+                                for (int kk = 0; kk < KB; ++kk) {
+                                    const float2 wk = wp[(size_t)(kb + kk) * wstride];
+#pragma unroll
+                                    for (int r = 0; r < RH; ++r) a2[r] = __ffma2_rn(wk, win[r + kk], a2[r]);
+                                }
+                            }
+#pragma unroll
+                            for (int r = 0; r < RH; ++r) acc[2 * r + par] = a2[r];
                         }
                     }
                 } else {
-                    // dilation 2 (stride 1): outputs of one parity share an every-other-row window
+                    // residual branch: the block input itself (1x1 conv only)
 #pragma unroll
-                    for (int par = 0; par < 2; ++par) {
-                        constexpr int RH = R / 2;
-                        float2 a2[RH];
+                    for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
+                }
+                // the depthwise output is not zero beyond len; the following MaskedConv1d zeroes it
 #pragma unroll
-                        for (int r = 0; r < RH; ++r) a2[r] = make_float2(0.f, 0.f);
-#pragma unroll 1
-                        for (int kb = 0; kb < K; kb += KB) {
-                            constexpr int WIN = RH - 1 + KB;
-                            float2 win[WIN];
+                for (int r = 0; r < R; ++r)
+                    if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
+
+                mbar_wait(empty_b + sb, ((gc / BSTAGES) & 1) ^ 1);
+                unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
 #pragma unroll
-                            for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw + par + 2 * (kb + j)) * XP];
-#pragma unroll
-                            for (int kk = 0; kk < KB; ++kk) {
-                                const float2 wk = __ldg(wp + (size_t)(kb + kk) * wstride);
-#pragma unroll
-                                for (int r = 0; r < RH; ++r) a2[r] = __ffma2_rn(wk, win[r + kk], a2[r]);
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < RH; ++r) acc[2 * r + par] = a2[r];
+                for (int r = 0; r < R; ++r) {
+                    const int row = tw + r;
+                    const uint32_t off = sw64_offset(row, cp >> 2) + (cp & 3) * 4;
+                    const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
+                    *reinterpret_cast<__half2*>(bh + off) = h;
+                    if (NPART == 2) {
+                        const float2 hf = __half22float2(h);
+                        *reinterpret_cast<__half2*>(bh + PART_BYTES + off) = __floats2half2_rn(acc[r].x - hf.x, acc[r].y - hf.y);
                     }
                 }
-            } else {
-                // residual branch: the block input itself (1x1 conv only)
-#pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
-            }
-            // the depthwise output is not zero beyond len; the following MaskedConv1d zeroes it
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
-
-            mbar_wait(empty_b + sb, ((c / BSTAGES) & 1) ^ 1);
-            unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int row = tw + r;
-                const uint32_t off = sw64_offset(row, cp >> 2) + (cp & 3) * 4;
-                const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
-                *reinterpret_cast<__half2*>(bh + off) = h;
-                if (NPART == 2) {
-                    const float2 hf = __half22float2(h);
-                    *reinterpret_cast<__half2*>(bh + PART_BYTES + off) = __floats2half2_rn(acc[r].x - hf.x, acc[r].y - hf.y);
-                }
-            }
-            fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(full_b + sb); mbar_arrive(empty_x + sx); }
-        }
-
-        // ================= epilogue: TMEM -> registers -> +shift, ReLU, mask -> global (channels-last) =================
-        mbar_wait(acc_full, 0);
-        tcgen05_fence_after();
-        const int q = warp & 3, half = warp >> 2;
-        const int len_o = p.len_out[b];
-        for (int m = 0; m < p.nM; ++m) {
-            const int co = co0 + m * 128 + q * 32 + lane;
-            const float sh = __ldg(p.shift + co), sc = __ldg(p.wscale_inv + co);
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int col0 = half * 64 + j * 32;
-                uint32_t rg[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 128 + col0), rg);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int t = t0 + col0 + i;
-                    if (t < p.T_out) {
-                        float v = fmaf(__uint_as_float(rg[i]), sc, sh);
-                        if (p.relu) v = fmaxf(v, 0.f);
-                        if (p.mask_tail && t >= len_o) v = 0.f;
-                        p.out[((size_t)b * p.T_out + t) * p.Cout + co] = v;
-                    }
-                }
+                fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(full_b + sb); mbar_arrive(empty_x + sx); }
             }
         }
     }
@@ -397,7 +483,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     __syncthreads();
     if (warp == WARP_MMA) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
 }
 
@@ -444,23 +530,30 @@ static const KernelEntry* find_kernel(int K, int S, int D)
 }
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* stage_bytes)
+static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_off, int* stage_bytes)
 {
     const int rows = (TN - 1) * S + (K - 1) * D + 1;
     int nb = (rows + 255) / 256, br = (rows + nb - 1) / nb;
     br = (br + 7) / 8 * 8;
     int bytes = nb * br * KC * 4;
     if (bytes < TN * KC * 4) bytes = TN * KC * 4;            // residual / identity chunks load 128 rows
-    *n_xbox = nb; *xbox_rows = br; *stage_bytes = (bytes + 1023) / 1024 * 1024;
+    *n_xbox = nb; *xbox_rows = br; *w_off = bytes;
+    bytes += K * KC * 4;                                      // + the chunk's depthwise taps
+    *stage_bytes = (bytes + 1023) / 1024 * 1024;
 }
 
-static int pick_aslots(int npart, int x_stage_bytes, int nM)
+// ring depths under the 227 KiB budget: prefer a 3-deep activation window (TMA latency hiding), keep at
+// least one chunk (+1 slot) of weight look-ahead
+static void pick_rings(int npart, int x_stage_bytes, int nM, int* xstages, int* bstages, int* aslots)
 {
-    const int fixed = BSTAGES * PART_BYTES * npart + XSTAGES * x_stage_bytes + 1024 /*barriers*/ + 1024 /*align slack*/;
-    int slots = (SMEM_LIMIT - fixed) / (PART_BYTES * npart);
-    if (slots > 16) slots = 16;
-    if (slots > 2 * nM) slots = 2 * nM;                       // two chunks of look-ahead is plenty
-    return slots;
+    for (int xs = 3; xs >= 2; --xs) {
+        const int bs = 2;
+        const int fixed = bs * PART_BYTES * npart + xs * x_stage_bytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+        int slots = (SMEM_LIMIT - fixed) / (PART_BYTES * npart);
+        if (slots > 16) slots = 16;
+        if (slots > 2 * nM) slots = 2 * nM;                   // two chunks of look-ahead is plenty
+        if (slots >= nM + 1 || xs == 2) { *xstages = xs; *bstages = bs; *aslots = slots; return; }
+    }
 }
 
 }  // namespace tc
@@ -475,6 +568,9 @@ int tc_init()
     if (!fn || qres != cudaDriverEntryPointSuccess)
         return set_error(VASR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     g_encode = (EncodeTiledFn)fn;
+    int dev = 0;
+    VASR_CUDA_OK(cudaGetDevice(&dev));
+    VASR_CUDA_OK(cudaDeviceGetAttribute(&tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     for (const KernelEntry& e : g_kernels)
         for (int i = 0; i < 2; ++i)
             VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -555,7 +651,8 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
 }
 
 int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
-                       int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb, cudaStream_t st)
+                       int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
+                       int* tile_counter, cudaStream_t st)
 {
     using namespace tc;
     (void)len_in;
@@ -572,12 +669,12 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     p.n_main = sb.cin / KC; p.n_res = sb.has_res ? sb.res_cin / KC : 0;
     const int co_cta = sb.cout > MAX_CO_CTA ? MAX_CO_CTA : sb.cout;
     p.nM = co_cta / 128;
-    x_geometry(K, sb.stride, sb.dilation, &p.n_xbox, &p.xbox_rows, &p.x_stage_bytes);
+    x_geometry(K, sb.stride, sb.dilation, &p.n_xbox, &p.xbox_rows, &p.x_w_off, &p.x_stage_bytes);
     p.relu = sb.relu ? 1 : 0; p.mask_tail = sb.final_layer ? 0 : 1;
-    p.aslots = pick_aslots(npart, p.x_stage_bytes, p.nM);
+    pick_rings(npart, p.x_stage_bytes, p.nM, &p.xstages, &p.bstages, &p.aslots);
     if (p.aslots < 2) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
-    const size_t smem = (size_t)p.aslots * PART_BYTES * npart + (size_t)BSTAGES * PART_BYTES * npart +
-                        (size_t)XSTAGES * p.x_stage_bytes + 1024 + 1024;
+    const size_t smem = (size_t)p.aslots * PART_BYTES * npart + (size_t)p.bstages * PART_BYTES * npart +
+                        (size_t)p.xstages * p.x_stage_bytes + 1024 + 1024;
     p.b0 = b0;
     // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
     int rc;
@@ -592,7 +689,10 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
             sb.tmc_r = res_in;
         }
     }
-    dim3 grid(ceil_div(T_out, TN), sb.cout / co_cta, nb);
+    p.tile_counter = tile_counter;
+    p.n_tt = ceil_div(T_out, TN); p.n_utt = nb; p.n_cg = sb.cout / co_cta;
+    const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
+    dim3 grid(n_tiles < g_num_sms ? n_tiles : g_num_sms, 1, 1);      // persistent: at most one CTA per SM
     void* args[] = {(void*)sb.tm_x, (void*)(sb.has_res ? sb.tm_r : sb.tm_x), (void*)sb.tm_w_hi, (void*)sb.tm_w_lo,
                     (void*)sb.tm_r_hi, (void*)sb.tm_r_lo, (void*)&p};
     VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
