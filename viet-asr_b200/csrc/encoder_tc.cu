@@ -5,13 +5,16 @@
 // Restates one sub-block of JasperBlock.forward (nemo/collections/asr/parts/jasper.py:408-448) per launch.
 //
 // Tile: one utterance b, TN = 128 output time steps, up to 512 output channels
-//       D[co, t] (M = 128 co per MMA, N = 128 t) = W[co, ci] (A, K-major, TMA) x Act[t, ci] (B, K-major, written
-//       by the depthwise warps), chunked over ci in KC = 32 (64-byte fp16 rows -> SWIZZLE_64B).
+//       D[t, co] (M = 128 t, N = 256 co per MMA) = Act[t, ci] (A, K-major, written by the depthwise warps)
+//       x W[co, ci] (B, K-major, TMA), chunked over ci in KC = 32 (64-byte fp16 rows -> SWIZZLE_64B).
+//       N = 256 keeps the shared-memory operand traffic per MAC 25 % below the 128 x 128 shape and puts
+//       time on the TMEM lanes, so an epilogue thread owns one output row and stores 16-byte vectors.
 // Precision: fp16 operands with a 2-term split  x = hi + lo  on both sides and three products
 //       hi*hi + lo*hi + hi*lo  (fp32-grade, mode 1) or hi*hi only (mode 2).  Weights are pre-scaled per output
 //       channel by a power of two so that hi/lo stay in fp16's normal range; the scale is undone in the epilogue.
-// Warp roles (352 threads): 0..7 depthwise producers + epilogue, 8 = TMA producer of the activation window,
-//       9 = TMA producer of the weight slots, 10 = tcgen05.mma issuer (+ TMEM alloc/dealloc).
+// Warp roles (608 threads, persistent CTA): 0..7 depthwise producers, 8 = tile scheduler + TMA producer of the
+//       activation window, 9 = TMA producer of the weight slots, 10 = tcgen05.mma issuer (+ TMEM alloc/dealloc),
+//       11..18 epilogue (two warps per TMEM lane quarter).
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cuda.h>
@@ -19,6 +22,7 @@
 #include <vector>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace vasr {
 namespace tc {
@@ -26,13 +30,14 @@ namespace tc {
 constexpr int TN = 128;                 // output time steps per CTA
 constexpr int KC = 32;                  // input channels per chunk
 constexpr int NDW = 8;                  // depthwise warps 0..7
-constexpr int NEPI = 4;                 // epilogue warps 11..14: warp & 3 = 3,0,1,2 -> each TMEM lane quarter once
+constexpr int NEPI = 8;                 // epilogue warps 11..18: warp & 3 = 3,0,1,2,3,0,1,2 -> each TMEM lane quarter twice
 constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10, WARP_EPI = 11;
-constexpr int NTHREADS = 15 * 32;
+constexpr int NTHREADS = 19 * 32;
 constexpr int MAX_STAGES = 4;           // upper bound of the activation-window / B-operand ring depths
 constexpr int SCHED = 4;                // depth of the tile ring
 constexpr int SCHED_CONSUMERS = 1 /*A*/ + 1 /*MMA*/ + NDW + NEPI;
-constexpr int PART_BYTES = 128 * KC * 2;   // one [128 rows x 64 B] fp16 operand tile = 8 KiB
+constexpr int PART_BYTES = 128 * KC * 2;   // activation operand: [128 t rows x 64 B] fp16 = 8 KiB per part
+constexpr int W_PART = 256 * KC * 2;       // weight operand:     [256 co rows x 64 B] fp16 = 16 KiB per part
 constexpr int MAX_CO_CTA = 512;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -147,9 +152,9 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int c16)
     return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((c16 ^ ((row >> 1) & 3)) << 4));
 }
 
-// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=128 (cute UMMA::InstrDescriptor)
-constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) |
-                                         ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=256 (cute UMMA::InstrDescriptor)
+constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) |
+                                         ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct Params {
     const float* dw_w;       // [Cin/32][K][32] fp32 depthwise taps (ones for a plain 1x1 conv)
@@ -160,13 +165,17 @@ struct Params {
     int* tile_counter;       // dynamic tile scheduler (zeroed before the launch)
     int Cin, Cres, Cout, T_out, pad;
     int n_main, n_res;       // chunks of 32 input channels
-    int nM;                  // 128-row M blocks per tile (2 or 4)
+    int nN;                  // 256-column (output channel) N blocks per tile (1 or 2)
     int n_xbox, xbox_rows, x_stage_bytes, x_w_off;   // x_w_off: offset of the chunk's depthwise taps in a stage
     int xstages, bstages;
     int relu, mask_tail, aslots;
     int b0;                  // first utterance of this launch (sub-batch on its own stream)
     int n_tt, n_utt, n_cg;   // tiles: time tiles per utterance x utterances x output-channel groups
+    unsigned long long* prof; // optional [16] cycle counters (VASR_TC_PROF=1), see tools/
 };
+
+#define PROF_BEGIN() long long _pt = clock64()
+#define PROF_ADD(i) do { long long _n = clock64(); pacc[i] += (unsigned long long)(_n - _pt); _pt = _n; } while (0)
 
 // Persistent CTA (one per SM): tiles are claimed from an atomic counter by the scheduler thread and published
 // to the other roles through a small shared-memory ring; all operand rings and the TMEM accumulator buffers
@@ -181,7 +190,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve-up (every operand tile 1024-byte aligned; the launch reserves 1 KiB of slack for this round-up)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int A_SLOT = PART_BYTES * NPART, B_STAGE = PART_BYTES * NPART;
+    constexpr int A_SLOT = W_PART * NPART, B_STAGE = PART_BYTES * NPART;   // a_ring = weight slots, b_ring = activation stages
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
     unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
@@ -201,9 +210,10 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + SCHED);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long pacc[4] = {0ull, 0ull, 0ull, 0ull};
     const int nchunks = p.n_main + p.n_res;
     const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
-    const int acc_cols = p.nM * 128;                       // TMEM columns of one accumulator buffer
+    const int acc_cols = p.nN * 256;                       // TMEM columns of one accumulator buffer
     const int nbuf = (acc_cols <= 256) ? 2 : 1;            // double-buffered when it fits the 512 columns
 
     if (threadIdx.x == 0) {
@@ -234,7 +244,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int tt = tile % p.n_tt;
         const int r = tile / p.n_tt;
         b = p.b0 + r % p.n_utt;
-        co0 = (r / p.n_utt) * (p.nM * 128);
+        co0 = (r / p.n_utt) * (p.nN * 256);
         t0 = tt * TN;
     };
     // consumer side of the tile ring: returns the tile id (or -1 = no more work)
@@ -263,7 +273,9 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 decode(tile, co0, b, t0);
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int s = gc % XSTAGES;
+                    PROF_BEGIN();
                     mbar_wait(empty_x + s, ((gc / XSTAGES) & 1) ^ 1);
+                    PROF_ADD(0);
                     unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
                     if (c < p.n_main) {
                         mbar_arrive_expect_tx(full_x + s, (uint32_t)(p.n_xbox * p.xbox_rows * KC * 4 + K * KC * 4));
@@ -280,7 +292,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
         }
     } else if (warp == WARP_A) {
-        // ======== TMA producer: weight slots [128 co x 32 ci] fp16 hi (+ lo), SWIZZLE_64B ========
+        // ======== TMA producer: weight slots [256 co x 32 ci] fp16 hi (+ lo), SWIZZLE_64B ========
         int slot = 0; uint32_t ph = 0;
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
@@ -291,12 +303,14 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int c = 0; c < nchunks; ++c) {
                     const bool res = c >= p.n_main;
                     const int ci0 = (res ? c - p.n_main : c) * KC;
-                    for (int m = 0; m < p.nM; ++m) {
+                    for (int m = 0; m < p.nN; ++m) {
+                        PROF_BEGIN();
                         mbar_wait(empty_a + slot, ph ^ 1);
+                        PROF_ADD(0);
                         mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
-                        tma_load_2d(dst, res ? &tm_r_hi : &tm_w_hi, ci0, co0 + m * 128, full_a + slot);
-                        if (NPART == 2) tma_load_2d(dst + PART_BYTES, res ? &tm_r_lo : &tm_w_lo, ci0, co0 + m * 128, full_a + slot);
+                        tma_load_2d(dst, res ? &tm_r_hi : &tm_w_hi, ci0, co0 + m * 256, full_a + slot);
+                        if (NPART == 2) tma_load_2d(dst + W_PART, res ? &tm_r_lo : &tm_w_lo, ci0, co0 + m * 256, full_a + slot);
                         if (++slot == p.aslots) { slot = 0; ph ^= 1; }
                     }
                 }
@@ -312,31 +326,37 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (tile < 0) break;
             if (lane == 0) {
                 const int ab = ti % nbuf;
+                PROF_BEGIN();
                 mbar_wait(acc_empty + ab, ((ti / nbuf) & 1) ^ 1);     // epilogue has drained this accumulator buffer
+                PROF_ADD(2);
                 tcgen05_fence_after();
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int sb = gc % BSTAGES;
                     mbar_wait(full_b + sb, (gc / BSTAGES) & 1);
+                    PROF_ADD(0);
                     tcgen05_fence_after();
                     const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
-                    for (int m = 0; m < p.nM; ++m) {
+                    for (int m = 0; m < p.nN; ++m) {
                         mbar_wait(full_a + slot, ph);
+                        PROF_ADD(1);
                         tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
-                        const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 128);
+                        const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
+                        const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 256);
 #pragma unroll
                         for (int ks = 0; ks < KC / 16; ++ks) {
-                            const uint64_t a_hi = make_desc_sw64(a_addr + ks * 32);
-                            const uint64_t b_hi = make_desc_sw64(b_addr + ks * 32);
-                            umma_f16(d, a_hi, b_hi, IDESC_F16_M128_N128, (c > 0 || ks > 0) ? 1u : 0u);
+                            // A operand = activations (M = 128 time rows), B operand = weights (N = 256 channels)
+                            const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
+                            const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                            umma_f16(d, x_hi, w_hi, IDESC_F16_M128_N256, (c > 0 || ks > 0) ? 1u : 0u);
                             if (NPART == 2) {
-                                const uint64_t a_lo = make_desc_sw64(a_addr + PART_BYTES + ks * 32);
-                                const uint64_t b_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
-                                umma_f16(d, a_lo, b_hi, IDESC_F16_M128_N128, 1u);
-                                umma_f16(d, a_hi, b_lo, IDESC_F16_M128_N128, 1u);
+                                const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
+                                const uint64_t w_lo = make_desc_sw64(w_addr + W_PART + ks * 32);
+                                umma_f16(d, x_lo, w_hi, IDESC_F16_M128_N256, 1u);
+                                umma_f16(d, x_hi, w_lo, IDESC_F16_M128_N256, 1u);
                             }
                         }
                         tcgen05_commit(empty_a + slot);        // weight slot reusable once these MMAs retire
+                        PROF_ADD(3);
                         if (++slot == p.aslots) { slot = 0; ph ^= 1; }
                     }
                     tcgen05_commit(empty_b + sb);              // activation stage reusable
@@ -346,41 +366,52 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             __syncwarp();
         }
     } else if (warp >= WARP_EPI) {
-        // ======== epilogue (4 warps): TMEM -> registers -> +shift, ReLU, mask -> global (channels-last) ========
+        // ======== epilogue (8 warps): TMEM -> registers -> +shift, ReLU, mask -> global (channels-last) ========
+        // TMEM lane = time row, column = output channel: a thread owns one output row of the tile and writes
+        // 32 consecutive channels (128 bytes) per tcgen05.ld; the two warps of a lane quarter split the columns.
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int half = (warp - WARP_EPI) >> 2;               // which half of every N block's column groups
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
             if (tile < 0) break;
             int co0, b, t0;
             decode(tile, co0, b, t0);
             const int ab = ti % nbuf;
-            const int len_o = p.len_out[b];
+            const int t = t0 + q * 32 + lane;
+            const bool row_ok = t < p.T_out;
+            const bool live = !(p.mask_tail && t >= p.len_out[b]);
+            float* orow = p.out + ((size_t)b * p.T_out + (row_ok ? t : 0)) * p.Cout + co0;
+            PROF_BEGIN();
             mbar_wait(acc_full + ab, (ti / nbuf) & 1);
+            PROF_ADD(0);
             tcgen05_fence_after();
-            for (int m = 0; m < p.nM; ++m) {
-                const int co = co0 + m * 128 + q * 32 + lane;
-                const float sh = __ldg(p.shift + co), sc = __ldg(p.wscale_inv + co);
+            for (int m = 0; m < p.nN; ++m) {
 #pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
-                    const int col0 = j * 32;
+                    const int col0 = m * 256 + (half * 4 + j) * 32;
                     uint32_t rg[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + m * 128 + col0), rg);
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + col0), rg);
+                    const float4* sc4 = reinterpret_cast<const float4*>(p.wscale_inv + co0 + col0);
+                    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + co0 + col0);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int t = t0 + col0 + i;
-                        if (t < p.T_out) {
-                            float v = fmaf(__uint_as_float(rg[i]), sc, sh);
-                            if (p.relu) v = fmaxf(v, 0.f);
-                            if (p.mask_tail && t >= len_o) v = 0.f;
-                            p.out[((size_t)b * p.T_out + t) * p.Cout + co] = v;
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);     // warp-uniform addresses (broadcast)
+                        float4 v;
+                        v.x = fmaf(__uint_as_float(rg[4 * i + 0]), sc.x, sh.x);
+                        v.y = fmaf(__uint_as_float(rg[4 * i + 1]), sc.y, sh.y);
+                        v.z = fmaf(__uint_as_float(rg[4 * i + 2]), sc.z, sh.z);
+                        v.w = fmaf(__uint_as_float(rg[4 * i + 3]), sc.w, sh.w);
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) *reinterpret_cast<float4*>(orow + col0 + 4 * i) = v;
                     }
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + ab);        // accumulator buffer may be overwritten
+            PROF_ADD(1);
         }
     } else if (warp < NDW) {
         // ======== depthwise producers (warps 0..7) ========
@@ -401,7 +432,9 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const int len_mid = p.len_out[b];    // the 1x1 conv masks its input rows t >= len (parts/jasper.py:116)
             for (int c = 0; c < nchunks; ++c, ++gc) {
                 const int sx = gc % XSTAGES, sb = gc % BSTAGES;
+                PROF_BEGIN();
                 mbar_wait(full_x + sx, (gc / XSTAGES) & 1);
+                PROF_ADD(0);
                 const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
                 float2 acc[R];
                 if (c < p.n_main) {
@@ -460,7 +493,9 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int r = 0; r < R; ++r)
                     if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
 
+                PROF_ADD(1);
                 mbar_wait(empty_b + sb, ((gc / BSTAGES) & 1) ^ 1);
+                PROF_ADD(2);
                 unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -476,8 +511,20 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 fence_proxy_async();             // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(full_b + sb); mbar_arrive(empty_x + sx); }
+                PROF_ADD(3);
             }
         }
+    }
+    if (p.prof && lane == 0) {
+        // slots: dw(warp 0) 0..3 = wait full_x / compute / wait empty_b / store; X producer 4 = wait empty_x;
+        // A producer 5 = wait empty_a; MMA 6..9 = wait full_b / wait full_a / wait acc_empty / issue+commit; epilogue 10..11 = wait acc_full / drain
+        int base = -1;
+        if (warp == 0) base = 0; else if (warp == WARP_X) base = 4; else if (warp == WARP_A) base = 5;
+        else if (warp == WARP_MMA) base = 6; else if (warp == WARP_EPI) base = 10;
+        if (base >= 0)
+            for (int i = 0; i < 4; ++i)
+                if (pacc[i]) atomicAdd(p.prof + base + i, pacc[i]);
+        if (warp == 1) atomicAdd(p.prof + 15, 1ull);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -507,12 +554,12 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, i
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
-// weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 128), SWIZZLE_64B
+// weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 256), SWIZZLE_64B
 static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin)
 {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)Cout};
     cuuint64_t str[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, 128};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 256};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
@@ -542,18 +589,22 @@ static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_
     *stage_bytes = (bytes + 1023) / 1024 * 1024;
 }
 
-// ring depths under the 227 KiB budget: prefer a 3-deep activation window (TMA latency hiding), keep at
-// least one chunk (+1 slot) of weight look-ahead
-static void pick_rings(int npart, int x_stage_bytes, int nM, int* xstages, int* bstages, int* aslots)
+// ring depths under the 227 KiB budget.  The tensor-core side (weight TMA latency + MMA) is the critical path
+// (profiles/), so the weight ring gets the capacity: 2 activation-window stages (3 when there is room), 2
+// activation-operand stages, and as many 256-channel weight slots as fit (at least one chunk, at most four chunks).
+static void pick_rings(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots)
 {
-    for (int xs = 3; xs >= 2; --xs) {
-        const int bs = 2;
-        const int fixed = bs * PART_BYTES * npart + xs * x_stage_bytes + 1024 /*barriers*/ + 1024 /*align slack*/;
-        int slots = (SMEM_LIMIT - fixed) / (PART_BYTES * npart);
-        if (slots > 16) slots = 16;
-        if (slots > 2 * nM) slots = 2 * nM;                   // two chunks of look-ahead is plenty
-        if (slots >= nM + 1 || xs == 2) { *xstages = xs; *bstages = bs; *aslots = slots; return; }
-    }
+    const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
+    const int overhead = 1024 /*barriers*/ + 1024 /*align slack*/;
+    int xs = 2, bs = 2;
+    int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
+    if (slots > 4 * nN) slots = 4 * nN;
+    if (slots > 16) slots = 16;
+    // spend what is left on a third activation-window stage, then a third operand stage
+    int left = SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes - slots * w_slot;
+    if (left >= x_stage_bytes) { xs = 3; left -= x_stage_bytes; }
+    if (left >= b_stage) { bs = 3; left -= b_stage; }
+    *xstages = xs; *bstages = bs; *aslots = slots;
 }
 
 }  // namespace tc
@@ -583,7 +634,7 @@ bool subblock_tc_supported(const SubBlock& sb)
     const int K = sb.separable ? sb.kernel : 1;
     if (!find_kernel(K, sb.stride, sb.dilation)) return false;
     if (sb.cin % KC != 0 || (sb.has_res && sb.res_cin % KC != 0)) return false;
-    if (sb.cout % 256 != 0) return false;                      // nM in {2, 4} (TMEM columns a power of two)
+    if (sb.cout % 256 != 0) return false;                      // N blocks of 256 output channels
     if (sb.cout > MAX_CO_CTA && sb.cout % MAX_CO_CTA != 0) return false;
     if (sb.has_res && sb.stride != 1) return false;
     return true;
@@ -668,12 +719,12 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     p.pad = sb.separable ? sb.pad : 0;
     p.n_main = sb.cin / KC; p.n_res = sb.has_res ? sb.res_cin / KC : 0;
     const int co_cta = sb.cout > MAX_CO_CTA ? MAX_CO_CTA : sb.cout;
-    p.nM = co_cta / 128;
+    p.nN = co_cta / 256;
     x_geometry(K, sb.stride, sb.dilation, &p.n_xbox, &p.xbox_rows, &p.x_w_off, &p.x_stage_bytes);
     p.relu = sb.relu ? 1 : 0; p.mask_tail = sb.final_layer ? 0 : 1;
-    pick_rings(npart, p.x_stage_bytes, p.nM, &p.xstages, &p.bstages, &p.aslots);
-    if (p.aslots < 2) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
-    const size_t smem = (size_t)p.aslots * PART_BYTES * npart + (size_t)p.bstages * PART_BYTES * npart +
+    pick_rings(npart, p.x_stage_bytes, p.nN, &p.xstages, &p.bstages, &p.aslots);
+    if (p.aslots < p.nN) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
+    const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
                         (size_t)p.xstages * p.x_stage_bytes + 1024 + 1024;
     p.b0 = b0;
     // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
@@ -695,8 +746,27 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     dim3 grid(n_tiles < g_num_sms ? n_tiles : g_num_sms, 1, 1);      // persistent: at most one CTA per SM
     void* args[] = {(void*)sb.tm_x, (void*)(sb.has_res ? sb.tm_r : sb.tm_x), (void*)sb.tm_w_hi, (void*)sb.tm_w_lo,
                     (void*)sb.tm_r_hi, (void*)sb.tm_r_lo, (void*)&p};
+    static int prof_on = -1;
+    static unsigned long long* d_prof = nullptr;
+    if (prof_on < 0) {
+        const char* e = getenv("VASR_TC_PROF");
+        prof_on = (e && atoi(e) > 0) ? 1 : 0;
+        if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    }
+    p.prof = prof_on ? d_prof : nullptr;
+    if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (prof_on) {
+        unsigned long long h[16];
+        VASR_CUDA_OK(cudaStreamSynchronize(st));
+        VASR_CUDA_OK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        const double n = (double)(h[15] ? h[15] : 1);
+        fprintf(stderr, "TCPROF k=%d cin=%d cout=%d res=%d tiles=%d ctas=%d xs=%d bs=%d as=%d | dw: wait_x %.0f comp %.0f wait_b %.0f store %.0f | xprod wait %.0f | aprod wait %.0f | mma: wait_b %.0f wait_a %.0f wait_acc %.0f issue %.0f | epi: wait %.0f drain %.0f (kcycles per CTA)\n",
+                K, sb.cin, sb.cout, (int)sb.has_res, n_tiles, (int)grid.x, p.xstages, p.bstages, p.aslots,
+                h[0] / n / 1e3, h[1] / n / 1e3, h[2] / n / 1e3, h[3] / n / 1e3, h[4] / n / 1e3, h[5] / n / 1e3,
+                h[6] / n / 1e3, h[7] / n / 1e3, h[8] / n / 1e3, h[9] / n / 1e3, h[10] / n / 1e3, h[11] / n / 1e3);
+    }
     return VASR_OK;
 }
 
