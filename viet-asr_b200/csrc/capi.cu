@@ -50,7 +50,7 @@ struct vasr_model {
     std::vector<cudaStream_t> sub_streams;
     std::vector<cudaEvent_t> sub_events;
     cudaEvent_t fork_event = nullptr;
-    int max_sub = 4;
+    int max_sub = 2;   // measured on B200: 2 sub-batches beat 1 (tail overlap) and 4 (weight re-streaming)
     // scratch of vasr_transcribe_host (grown on demand)
     void* scratch = nullptr; size_t scratch_bytes = 0;
 };
