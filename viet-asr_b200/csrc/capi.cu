@@ -372,6 +372,10 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
         for (int s2 = 0; s2 < nsub; ++s2) VASR_CUDA_OK(cudaStreamWaitEvent(m->sub_streams[s2], m->fork_event, 0));
     }
 
+    // VASR_GRID_SPLIT=1: each of the nsub concurrent kernels gets 1/nsub of the SMs (kernels of different sub-batches
+    // then run side by side, out of phase, instead of back to back)
+    int grid_limit = 0;
+    if (nsub > 1) { const char* e = getenv("VASR_GRID_SPLIT"); if (e && atoi(e) > 0) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); grid_limit = sms / nsub; } }
     const float* cur = feat;
     const float* block_in = feat;
     int T = T_f;
@@ -396,7 +400,7 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
                     if (b1 == b0) continue;
                     if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
                                                  m->gemm_mode == VASR_GEMM_F16X3, b0, b1 - b0,
-                                                 counters + li * 8 + s2,
+                                                 counters + li * 8 + s2, grid_limit,
                                                  nsub > 1 ? m->sub_streams[s2] : st))) return rc;
                 }
             } else {

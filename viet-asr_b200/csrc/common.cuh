@@ -74,6 +74,8 @@ struct SubBlock {
     alignas(64) unsigned char tm_x[128];
     alignas(64) unsigned char tm_r[128];
     const void* tmc_x = nullptr; const void* tmc_r = nullptr; int tmc_B = 0, tmc_T = 0;
+    alignas(64) unsigned char tm_y[128];      // output tensor map of the TMA-store epilogue
+    const void* tmc_y = nullptr; int tmc_yB = 0, tmc_yT = 0;
 };
 
 }  // namespace vasr

@@ -39,6 +39,7 @@ constexpr int SCHED_CONSUMERS = 1 /*A*/ + 1 /*MMA*/ + NDW + NEPI;
 constexpr int PART_BYTES = 128 * KC * 2;   // activation operand: [128 t rows x 64 B] fp16 = 8 KiB per part
 constexpr int W_PART = 256 * KC * 2;       // weight operand:     [256 co rows x 64 B] fp16 = 16 KiB per part
 constexpr int MAX_CO_CTA = 512;
+constexpr int EPI_STAGE_BYTES = TN * 32 * 4;   // one 128-row x 32-channel fp32 output slice (SWIZZLE_128B)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -99,6 +100,19 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
 {
@@ -172,6 +186,8 @@ struct Params {
     int b0;                  // first utterance of this launch (sub-batch on its own stream)
     int n_tt, n_utt, n_cg;   // tiles: time tiles per utterance x utterances x output-channel groups
     unsigned long long* prof; // optional [16] cycle counters (VASR_TC_PROF=1), see tools/
+    int tma_epi;              // 1: epilogue stages 128 x 32 output slices in smem and stores them with TMA
+    int dbg;                  // timing experiments only (VASR_TC_DBG): 1 = skip MMAs, 2 = skip depthwise FMAs, 4 = skip epilogue stores
 };
 
 #define PROF_BEGIN() long long _pt = clock64()
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_r,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
-                const Params p)
+                const __grid_constant__ CUtensorMap tm_out, const Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve-up (every operand tile 1024-byte aligned; the launch reserves 1 KiB of slack for this round-up)
@@ -194,7 +210,8 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
     unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + (size_t)p.xstages * p.x_stage_bytes);
+    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;      // [2][128 rows x 128 B] when tma_epi
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (p.tma_epi ? 2 * EPI_STAGE_BYTES : 0));
     const int XSTAGES = p.xstages, BSTAGES = p.bstages;
     uint64_t* full_x = bars;                 // [xstages]  TMA -> dw warps
     uint64_t* empty_x = full_x + MAX_STAGES; // [xstages]  dw warps -> TMA
@@ -229,6 +246,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (warp == WARP_X && lane == 0) { tma_prefetch_desc(&tm_x); if (p.n_res) tma_prefetch_desc(&tm_r); }
+    if (warp == WARP_EPI && lane == 0 && p.tma_epi) tma_prefetch_desc(&tm_out);
     if (warp == WARP_A && lane == 0) {
         tma_prefetch_desc(&tm_w_hi);
         if (NPART == 2) tma_prefetch_desc(&tm_w_lo);
@@ -347,6 +365,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                             // A operand = activations (M = 128 time rows), B operand = weights (N = 256 channels)
                             const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
                             const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                            if (p.dbg & 1) continue;
                             umma_f16(d, x_hi, w_hi, IDESC_F16_M128_N256, (c > 0 || ks > 0) ? 1u : 0u);
                             if (NPART == 2) {
                                 const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
@@ -371,48 +390,74 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // 32 consecutive channels (128 bytes) per tcgen05.ld; the two warps of a lane quarter split the columns.
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int half = (warp - WARP_EPI) >> 2;               // which half of every N block's column groups
+        const int row = q * 32 + lane;                         // tile row (time) owned by this thread
+        const bool issuer = (q == 0 && lane == 0);             // one thread per half-group drives its TMA stores
+        unsigned char* stage = epi_stage + half * EPI_STAGE_BYTES;
+        const int nslice = p.nN * 4;                           // 32-column slices handled by this half-group
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
             if (tile < 0) break;
             int co0, b, t0;
             decode(tile, co0, b, t0);
             const int ab = ti % nbuf;
-            const int t = t0 + q * 32 + lane;
+            const int t = t0 + row;
             const bool row_ok = t < p.T_out;
             const bool live = !(p.mask_tail && t >= p.len_out[b]);
             float* orow = p.out + ((size_t)b * p.T_out + (row_ok ? t : 0)) * p.Cout + co0;
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
+            auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
+            // +shift (BN), ReLU, length mask on one 32-channel slice held in registers, then out
+            auto finish = [&](uint32_t (&rg)[32], int col0) {
+                const float4* sc4 = reinterpret_cast<const float4*>(p.wscale_inv + co0 + col0);
+                const float4* sh4 = reinterpret_cast<const float4*>(p.shift + co0 + col0);
+                if (p.tma_epi) {
+                    if (issuer) bulk_wait_read0();             // previous slice has left the staging buffer
+                    named_bar_sync(1 + half, 128);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);     // warp-uniform addresses (broadcast)
+                    float4 v;
+                    v.x = fmaf(__uint_as_float(rg[4 * i + 0]), sc.x, sh.x);
+                    v.y = fmaf(__uint_as_float(rg[4 * i + 1]), sc.y, sh.y);
+                    v.z = fmaf(__uint_as_float(rg[4 * i + 2]), sc.z, sh.z);
+                    v.w = fmaf(__uint_as_float(rg[4 * i + 3]), sc.w, sh.w);
+                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.tma_epi)                             // 128-byte rows, 16-byte chunks XOR-swizzled by row (SWIZZLE_128B)
+                        *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
+                    else if (row_ok && !(p.dbg & 4))
+                        *reinterpret_cast<float4*>(orow + col0 + 4 * i) = v;
+                }
+                if (p.tma_epi) {
+                    fence_proxy_async();
+                    named_bar_sync(1 + half, 128);
+                    if (issuer && !(p.dbg & 4)) { tma_store_3d(&tm_out, stage, co0 + col0, t0, b); bulk_commit(); }
+                }
+            };
             PROF_BEGIN();
             mbar_wait(acc_full + ab, (ti / nbuf) & 1);
             PROF_ADD(0);
             tcgen05_fence_after();
-            for (int m = 0; m < p.nN; ++m) {
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(0), ra);
 #pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    const int col0 = m * 256 + (half * 4 + j) * 32;
-                    uint32_t rg[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + col0), rg);
-                    const float4* sc4 = reinterpret_cast<const float4*>(p.wscale_inv + co0 + col0);
-                    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + co0 + col0);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);     // warp-uniform addresses (broadcast)
-                        float4 v;
-                        v.x = fmaf(__uint_as_float(rg[4 * i + 0]), sc.x, sh.x);
-                        v.y = fmaf(__uint_as_float(rg[4 * i + 1]), sc.y, sh.y);
-                        v.z = fmaf(__uint_as_float(rg[4 * i + 2]), sc.z, sh.z);
-                        v.w = fmaf(__uint_as_float(rg[4 * i + 3]), sc.w, sh.w);
-                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok) *reinterpret_cast<float4*>(orow + col0 + 4 * i) = v;
-                    }
+            for (int sidx = 0; sidx < nslice; sidx += 2) {     // software-pipelined: the next slice's TMEM load is in flight
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(sidx + 1), rb);
+                finish(ra, slice_col(sidx));
+                tmem_ld_wait();
+                if (sidx + 2 < nslice) tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(sidx + 2), ra);
+                else {                                         // every TMEM read of this tile has completed
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + ab);
                 }
+                finish(rb, slice_col(sidx + 1));
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + ab);        // accumulator buffer may be overwritten
             PROF_ADD(1);
         }
+        if (p.tma_epi && issuer) bulk_wait_all0();
     } else if (warp < NDW) {
         // ======== depthwise producers (warps 0..7) ========
         // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R = 8 outputs:
@@ -437,12 +482,42 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 PROF_ADD(0);
                 const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
                 float2 acc[R];
-                if (c < p.n_main) {
+                if (p.dbg & 2) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
+                } else if (c < p.n_main) {
                     // depthwise taps of this chunk [K][32 ch], staged in shared memory next to the window
                     const float2* wp = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes + p.x_w_off) + cp;
                     constexpr int wstride = KC / 2;
-                    if (D == 1) {
-                        // window row of (output r, tap k) = (tw + r) * S + k
+                    if (S == 1) {
+                        // Rolling register window, fully unrolled over the taps: window slot of (output r, tap k) holds
+                        // row tw + r + k*D.  Each tap consumes R FFMA2 and refills D rows + 1 tap weight that are needed
+                        // P taps later, so shared-memory loads are spread evenly between the FMAs (no load/compute phases
+                        // shared by all warps) and only R + D*P rows are live.
+                        constexpr int P = 4;
+                        constexpr int WN = R + D * P;
+                        constexpr int LAST_ROW = (K - 1) * D + R - 1;
+                        float2 win[WN], wq[P];
+#pragma unroll
+                        for (int j = 0; j < WN; ++j) win[j] = (j <= LAST_ROW) ? xs[(size_t)(tw + j) * XP] : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < P; ++j) wq[j] = (j < K) ? wp[(size_t)j * wstride] : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const float2 wk = wq[k % P];
+                            if (k + P < K) wq[k % P] = wp[(size_t)(k + P) * wstride];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[(k * D + r) % WN], acc[r]);
+#pragma unroll
+                            for (int d = 0; d < D; ++d) {
+                                const int row = k * D + d + WN;                  // replaces the row that just went dead
+                                if (row <= LAST_ROW) win[(k * D + d) % WN] = xs[(size_t)(tw + row) * XP];
+                            }
+                        }
+                    } else {
+                        // stride 2 (first block only, 2 chunks): tap-blocked window, row of (r, k) = (tw + r) * S + k
 #pragma unroll
                         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
 #pragma unroll 1
@@ -457,30 +532,6 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                                 for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[r * S + kk], acc[r]);
                             }
-                        }
-                    } else {
-                        // dilation 2 (stride 1): outputs of one parity share an every-other-row window
-#pragma unroll
-                        for (int par = 0; par < 2; ++par) {
-                            constexpr int RH = R / 2;
-                            float2 a2[RH];
-#pragma unroll
-                            for (int r = 0; r < RH; ++r) a2[r] = make_float2(0.f, 0.f);
-#pragma unroll 1
-                            for (int kb = 0; kb < K; kb += KB) {
-                                constexpr int WIN = RH - 1 + KB;
-                                float2 win[WIN];
-#pragma unroll
-                                for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw + par + 2 * (kb + j)) * XP];
-#pragma unroll
-                                for (int kk = 0; kk < KB; ++kk) {
-                                    const float2 wk = wp[(size_t)(kb + kk) * wstride];
-#pragma unroll
-                                    for (int r = 0; r < RH; ++r) a2[r] = __ffma2_rn(wk, win[r + kk], a2[r]);
-                                }
-                            }
-#pragma unroll
-                            for (int r = 0; r < RH; ++r) acc[2 * r + par] = a2[r];
                         }
                     }
                 } else {
@@ -554,6 +605,14 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, i
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
+// output [B, T, C] fp32 -> 3-D map (C, T, B), box (32, 128, 1), SWIZZLE_128B (rows beyond T are clipped by the TMA)
+static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C)
+{
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)TN, 1};
+    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
 // weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 256), SWIZZLE_64B
 static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin)
 {
@@ -592,10 +651,10 @@ static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_
 // ring depths under the 227 KiB budget.  The tensor-core side (weight TMA latency + MMA) is the critical path
 // (profiles/), so the weight ring gets the capacity: 2 activation-window stages (3 when there is room), 2
 // activation-operand stages, and as many 256-channel weight slots as fit (at least one chunk, at most four chunks).
-static void pick_rings(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots)
+static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int* xstages, int* bstages, int* aslots)
 {
     const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
-    const int overhead = 1024 /*barriers*/ + 1024 /*align slack*/;
+    const int overhead = 1024 /*barriers*/ + 1024 /*align slack*/ + epi_bytes;
     int xs = 2, bs = 2;
     int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
     if (slots > 4 * nN) slots = 4 * nN;
@@ -703,7 +762,7 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
 
 int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
-                       int* tile_counter, cudaStream_t st)
+                       int* tile_counter, int grid_limit, cudaStream_t st)
 {
     using namespace tc;
     (void)len_in;
@@ -722,10 +781,16 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     p.nN = co_cta / 256;
     x_geometry(K, sb.stride, sb.dilation, &p.n_xbox, &p.xbox_rows, &p.x_w_off, &p.x_stage_bytes);
     p.relu = sb.relu ? 1 : 0; p.mask_tail = sb.final_layer ? 0 : 1;
-    pick_rings(npart, p.x_stage_bytes, p.nN, &p.xstages, &p.bstages, &p.aslots);
+    // TMA-store epilogue when its 32 KiB of staging still leaves one chunk of weight slots; direct stores otherwise
+    p.tma_epi = 1;
+    pick_rings(npart, p.x_stage_bytes, p.nN, 2 * EPI_STAGE_BYTES, &p.xstages, &p.bstages, &p.aslots);
+    if (p.aslots < p.nN || getenv("VASR_TC_NO_TMA_EPI")) {
+        p.tma_epi = 0;
+        pick_rings(npart, p.x_stage_bytes, p.nN, 0, &p.xstages, &p.bstages, &p.aslots);
+    }
     if (p.aslots < p.nN) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
     const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
-                        (size_t)p.xstages * p.x_stage_bytes + 1024 + 1024;
+                        (size_t)p.xstages * p.x_stage_bytes + 1024 + 1024 + (p.tma_epi ? 2 * EPI_STAGE_BYTES : 0);
     p.b0 = b0;
     // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
     int rc;
@@ -743,9 +808,15 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     p.tile_counter = tile_counter;
     p.n_tt = ceil_div(T_out, TN); p.n_utt = nb; p.n_cg = sb.cout / co_cta;
     const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
-    dim3 grid(n_tiles < g_num_sms ? n_tiles : g_num_sms, 1, 1);      // persistent: at most one CTA per SM
+    if (sb.tmc_y != y || sb.tmc_yB != B || sb.tmc_yT != T_out) {
+        if ((rc = encode_out((CUtensorMap*)sb.tm_y, y, B, T_out, sb.cout))) return rc;
+        sb.tmc_y = y; sb.tmc_yB = B; sb.tmc_yT = T_out;
+    }
+    int max_ctas = g_num_sms;                                        // persistent: at most one CTA per SM
+    if (grid_limit > 0 && grid_limit < max_ctas) max_ctas = grid_limit;   // concurrent sub-batch kernels share the SMs
+    dim3 grid(n_tiles < max_ctas ? n_tiles : max_ctas, 1, 1);
     void* args[] = {(void*)sb.tm_x, (void*)(sb.has_res ? sb.tm_r : sb.tm_x), (void*)sb.tm_w_hi, (void*)sb.tm_w_lo,
-                    (void*)sb.tm_r_hi, (void*)sb.tm_r_lo, (void*)&p};
+                    (void*)sb.tm_r_hi, (void*)sb.tm_r_lo, (void*)sb.tm_y, (void*)&p};
     static int prof_on = -1;
     static unsigned long long* d_prof = nullptr;
     if (prof_on < 0) {
@@ -754,6 +825,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
         if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
     }
     p.prof = prof_on ? d_prof : nullptr;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);

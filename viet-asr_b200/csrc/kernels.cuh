@@ -25,7 +25,7 @@ int launch_ctc_collapse(const long long* ids, int B, int T, int blank, int* out_
 // tcgen05 fused sub-block (encoder_tc.cu); returns VASR_EINVAL when the shape is not built
 int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
-                       int* tile_counter, cudaStream_t st);
+                       int* tile_counter, int grid_limit, cudaStream_t st);
 bool subblock_tc_supported(const SubBlock& sb);
 int tc_init();
 // w_main [cout][cin], w_res [cout][res_cin] (or null): BN-scale-folded fp32 weights on the host
