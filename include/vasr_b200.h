@@ -147,6 +147,19 @@ int  vasr_greedy_argmax(const float* log_probs, int N, int V, int64_t* ids, void
 int  vasr_ctc_collapse(const int64_t* ids, int B, int T, int blank,
                        int32_t* out_ids, int32_t* out_len, void* stream);
 
+/* ---- CTC prefix beam search, no language model ------------------------- */
+/* BeamSearchDecoderWithLM.forward with lm_path=None (beam_search_decoder.py:95-102 -> pyctcdecode decode()).
+ * log_probs [B, T, V] f32 (all T frames are used, like the reference), blank = V-1 for NeMo vocabularies,
+ * space_id = index of ' ' in the vocabulary or -1.  out_ids [B, T] i32 (best text as symbol ids, -1 padded,
+ * single spaces, no leading space), out_len [B] i32, out_score [B] f32 (log score, may be NULL).
+ * beam_width <= 128; pyctcdecode defaults: token_min_logp = -5, beam_prune_logp = -10.
+ * KenLM rescoring is not built (third-party, parity unpinned - DESIGN.md). */
+size_t vasr_ctc_beam_workspace_bytes(int B, int T);
+int  vasr_ctc_beam_search(const float* log_probs, int B, int T, int V, int blank, int space_id,
+                          int beam_width, float token_min_logp, float beam_prune_logp,
+                          void* workspace, size_t workspace_bytes,
+                          int32_t* out_ids, int32_t* out_len, float* out_score, void* stream);
+
 /* ---- whole path, HOST buffers (the reference-facing plugin call) ------- */
 /* wave_host [B, L] f32 and length_host [B] i64 in (pinned or pageable) host memory;
  * out_ids_host [B, T_e] i32 (-1 padded) and out_len_host [B] i32 in host memory.

@@ -207,7 +207,7 @@ def test_host_route_equals_device_route(mode):
     r = eng.forward_device(wave.cuda(), length.cuda())
     ids_h, len_h = eng.transcribe_host_ids(wave.pin_memory(), length.pin_memory())
     assert torch.equal(ids_h, r["out_ids"].cpu()) and torch.equal(len_h, r["out_len"].cpu())
-    texts = eng.transcribe_batch([w[:n].numpy() for w, n in zip(wave, length)])
+    texts = eng.transcribe_batch([w[:n].numpy() for w, n in zip(wave, length)], decoder="greedy")
     assert texts == V.ids_to_text(ids_h, len_h, md["labels"])
 
 
@@ -307,3 +307,67 @@ def test_full_size_batch_properties(mode):
         row = out[b, : n[b]]
         assert (row != blank).all() and (row >= 0).all()
     assert O.ctc_collapse(ids1[:4].cpu().numpy(), blank) == [out[b, : n[b]].tolist() for b in range(4)]
+
+
+# ----------------------------------------------------------------------------- beam search (no LM)
+@pytest.mark.parametrize("beam_width", [1, 8, 20, 128])
+def test_beam_search_matches_oracle_on_model_posteriors(beam_width):
+    """Kernel vs oracle/beam_oracle.py (a restatement of pyctcdecode without LM - parity UNPINNED against the
+    package itself) on the reference-generated log-probs of real speech and of the random-weight model."""
+    V = _cuda()
+    from oracle import beam_oracle as BO
+    for name, labels in (("vi12x1_real_batch", V.configs.VI_LABELS), ("en15x5_rand", V.configs.EN_LABELS),
+                         ("vi12x1_rand", V.configs.VI_LABELS)):
+        g = load_golden(name)
+        lp = torch.from_numpy(g["logits"]).log_softmax(-1)
+        ids, n, score = V.ctc_beam_search(lp.cuda(), labels, beam_width)
+        got = [" ".join(t.split()) for t in V.ids_to_text(ids, n, labels)]
+        for b in range(lp.shape[0]):
+            want, want_score = BO.beam_search_no_lm(lp[b].numpy(), labels, beam_width)
+            assert got[b] == want, (name, b, beam_width)
+            assert abs(score[b].item() - want_score) < 1e-3 * max(1.0, abs(want_score))
+
+
+def test_beam_search_edge_cases():
+    V = _cuda()
+    from oracle import beam_oracle as BO
+    labels = V.configs.EN_LABELS            # index 0 is ' '
+    g = torch.Generator().manual_seed(3)
+    T, V1 = 60, len(labels) + 1
+    cases = []
+    flat = torch.zeros(T, V1).log_softmax(-1)                           # flat posterior: > 16 candidates per frame
+    cases.append(flat)
+    peaky = torch.full((T, V1), -30.0); peaky[:, V1 - 1] = 0.0          # all blank -> empty text
+    cases.append(peaky.log_softmax(-1))
+    sp = torch.full((T, V1), -30.0); sp[:, 0] = 0.0                     # all spaces -> empty text after normalisation
+    cases.append(sp.log_softmax(-1))
+    rnd = (3.0 * torch.randn(T, V1, generator=g)).log_softmax(-1)       # diffuse random posterior
+    cases.append(rnd)
+    word = torch.full((T, V1), -12.0)
+    for t, c in enumerate([8, 8, 28, 9, 0, 0, 28, 0, 20, 8, 5, 18, 5] + [28] * (T - 13)):   # "hi there" with doubled spaces
+        word[t, c] = 0.0
+    cases.append(word.log_softmax(-1))
+    lp = torch.stack(cases)
+    ids, n, _ = V.ctc_beam_search(lp.cuda(), labels, 16)
+    got = [" ".join(t.split()) for t in V.ids_to_text(ids, n, labels)]
+    want = [BO.beam_search_no_lm(x.numpy(), labels, 16)[0] for x in lp]
+    assert got == want
+    assert got[1] == "" and got[2] == "" and got[4] == "hi there"
+
+
+def test_beam_module_and_engine():
+    V = _cuda()
+    from oracle import beam_oracle as BO
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "rand")
+    eng = _engine(V, md, enc_sd, dec_sd, "fp32")
+    with pytest.raises(NotImplementedError):
+        V.BeamSearchDecoderWithLM(lm_path="3-gram-lm.binary", vocab=md["labels"], beam_width=20, alpha=0.5, beta=1.5, num_cpus=1)
+    g = load_golden("vi12x1_rand")
+    wave, length = pcm_to_wave(g["pcm16"]), torch.from_numpy(g["lens"])
+    r = eng.forward_device(wave.cuda(), length.cuda(), want_log_probs=True)
+    dec = V.BeamSearchDecoderWithLM(lm_path=None, vocab=md["labels"], beam_width=20, alpha=0.5, beta=1.5, num_cpus=1)
+    one = dec.forward(log_probs=r["log_probs"][:1], log_probs_length=r["enc_len"][:1])
+    assert isinstance(one, str)                                           # the reference returns one string for its batch of 1
+    assert one == BO.beam_search_no_lm(r["log_probs"][0].cpu().numpy(), md["labels"], 20)[0]
+    both = eng.transcribe_batch([w[:n].numpy() for w, n in zip(wave, length)])   # engine default: beam search, no LM
+    assert both == [BO.beam_search_no_lm(x.cpu().numpy(), md["labels"], 20)[0] for x in r["log_probs"]]

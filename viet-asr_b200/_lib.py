@@ -52,6 +52,8 @@ PROTOTYPES = {
     "vasr_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "vasr_greedy_argmax": (_i, [_vp, _i, _i, _vp, _vp]),
     "vasr_ctc_collapse": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "vasr_ctc_beam_workspace_bytes": (_sz, [_i, _i]),
+    "vasr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vasr_transcribe_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
 }
 

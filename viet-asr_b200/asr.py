@@ -478,6 +478,68 @@ class GreedyCTCDecoder(TrainableNM):
         return out
 
 
+# --------------------------------------------------------------------------- beam search
+def ctc_beam_search(log_probs: torch.Tensor, vocab: Sequence[str], beam_width: int,
+                    token_min_logp: float = -5.0, beam_prune_logp: float = -10.0):
+    """Device prefix beam search (no LM): log_probs [B, T, V+1] -> (ids [B, T] i32, len [B] i32, score [B] f32)."""
+    _require_cuda(log_probs, "ctc_beam_search")
+    lp = log_probs.to(torch.float32).contiguous()
+    B, T, V1 = lp.shape
+    if V1 != len(vocab) + 1:
+        raise ValueError(f"log_probs has {V1} classes but the vocabulary has {len(vocab)} labels (+1 blank)")
+    lib = _lib.load()
+    ws = torch.empty((int(lib.vasr_ctc_beam_workspace_bytes(B, T)),), dtype=torch.uint8, device=lp.device)
+    ids = torch.empty((B, T), dtype=torch.int32, device=lp.device)
+    n = torch.empty((B,), dtype=torch.int32, device=lp.device)
+    sc = torch.empty((B,), dtype=torch.float32, device=lp.device)
+    space_id = list(vocab).index(" ") if " " in vocab else -1
+    _lib.check(lib.vasr_ctc_beam_search(lp.data_ptr(), B, T, V1, len(vocab), space_id, int(beam_width),
+                                        float(token_min_logp), float(beam_prune_logp), ws.data_ptr(), ws.numel(),
+                                        ids.data_ptr(), n.data_ptr(), sc.data_ptr(), _stream_ptr()))
+    return ids, n, sc
+
+
+class BeamSearchDecoderWithLM(NonTrainableNM):
+    """nemo/collections/asr/beam_search_decoder.py:14-102, for `lm_path=None` - the mode infer.py:118-130 falls
+    back to when kenlm is not importable: pyctcdecode's prefix beam search without a language model, here as
+    a batched CUDA kernel (the reference is CPU-only and asserts batch size 1, :96).  `log_probs_length` is
+    ignored like in the reference (:95-101).  KenLM rescoring (`lm_path` set) is NOT built: pyctcdecode and
+    kenlm are un-vendored third-party packages and the shipped LMs are quantised KenLM binaries
+     - asking for it raises NotImplementedError instead of silently decoding without it."""
+
+    @property
+    def input_ports(self):
+        return {"log_probs": NeuralType(("B", "T", "D"), LogprobsType()),
+                "log_probs_length": NeuralType(tuple("B"), LengthsType())}
+
+    @property
+    def output_ports(self):
+        return {"predictions": NeuralType(("B", "T"), PredictionsType())}
+
+    def __init__(self, lm_path, vocab, beam_width, alpha, beta, num_cpus, cutoff_prob=1.0, cutoff_top_n=40,
+                 input_tensor=True):
+        super().__init__()
+        if self._factory.world_size > 1:
+            raise ValueError("BeamSearchDecoderWithLM does not run in distributed mode")   # beam_search_decoder.py:79-80
+        if lm_path is not None:
+            raise NotImplementedError("KenLM rescoring is not built in vasr_b200 (pass lm_path=None for beam search "
+                                      "without a language model)")
+        if not 1 <= int(beam_width) <= 128:
+            raise ValueError(f"beam_width must be in [1, 128], got {beam_width}")
+        self.vocab = list(vocab)
+        self.beam_width = int(beam_width)
+        self.alpha, self.beta = alpha, beta          # unused without an LM (kept for the constructor contract)
+        self.num_cpus, self.cutoff_prob, self.cutoff_top_n, self.input_tensor = num_cpus, cutoff_prob, cutoff_top_n, input_tensor
+
+    def decode_batch(self, log_probs) -> List[str]:
+        ids, n, _ = ctc_beam_search(log_probs, self.vocab, self.beam_width)
+        return [" ".join(t.split()) for t in ids_to_text(ids, n, self.vocab)]
+
+    def forward(self, log_probs, log_probs_length=None):
+        texts = self.decode_batch(log_probs)
+        return texts[0] if len(texts) == 1 else texts
+
+
 # --------------------------------------------------------------------------- helpers.py
 def ctc_collapse(predictions: torch.Tensor, blank: int):
     """Device CTC collapse -> (ids [B, T] int32 padded with -1, lengths [B] int32)."""

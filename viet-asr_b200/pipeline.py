@@ -27,12 +27,15 @@ class VietASR:
     def __init__(self, config_file: Optional[str] = None, encoder_checkpoint: Optional[str] = None,
                  decoder_checkpoint: Optional[str] = None, device: str = "gpu", lm_path: Optional[str] = None,
                  beam_width: int = 20, lm_alpha: float = 0.5, lm_beta: float = 1.5, *,
-                 model_definition: Optional[Dict] = None, gemm_mode: str = "fp32"):
+                 model_definition: Optional[Dict] = None, gemm_mode: str = "f16x3", decoder: str = "beam"):
         if device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("vasr_b200.VietASR runs on a CUDA device only (device='gpu'); there is no CPU path")
         if lm_path is not None:
-            raise NotImplementedError("beam search + KenLM rescoring is not built yet (SURVEY.md section 8f.1); "
-                                      "pass lm_path=None for the greedy path")
+            raise NotImplementedError("KenLM rescoring is not built (SURVEY.md section 8f.1); pass lm_path=None for beam "
+                                      "search without a language model (what infer.py:118-130 falls back to)")
+        if decoder not in ("beam", "greedy"):
+            raise ValueError(f"decoder must be 'beam' or 'greedy', got {decoder!r}")
+        self.decoder_kind = decoder
         if model_definition is None:
             if config_file is None:
                 raise ValueError("either config_file or model_definition is required")
@@ -49,6 +52,8 @@ class VietASR:
         self.decoder = asr.JasperDecoderForCTC(feat_in=md["JasperEncoder"]["jasper"][-1]["filters"],
                                                num_classes=len(self.labels))
         self.greedy = asr.GreedyCTCDecoder()
+        self.beam = asr.BeamSearchDecoderWithLM(lm_path=None, vocab=self.labels, beam_width=beam_width,
+                                                alpha=lm_alpha, beta=lm_beta, num_cpus=1)
         self.encoder.attach_decoder(self.decoder)
         if encoder_checkpoint:
             self.encoder.restore_from(encoder_checkpoint)
@@ -100,17 +105,30 @@ class VietASR:
                                               torch.cuda.current_stream().cuda_stream))
         return out_ids, out_len
 
-    def transcribe_batch(self, signals: Sequence[np.ndarray]) -> List[str]:
+    @torch.no_grad()
+    def beam_batch_device(self, wave: torch.Tensor, length: torch.Tensor) -> List[str]:
+        """Device tensors -> transcripts through the beam-search decoder (no LM), batched."""
+        feat, seq = self.preprocessor.forward_channels_last(wave, length)
+        enc, _ = self.encoder.forward_channels_last(feat, seq)
+        logp, _ = self.decoder.forward_channels_last(enc, True)
+        return self.beam.decode_batch(logp)
+
+    def transcribe_batch(self, signals: Sequence[np.ndarray], decoder: Optional[str] = None) -> List[str]:
         """List of 1-D float waveforms (16 kHz) -> transcripts; zero-pads to the longest
-        (the `seq_collate_fn` convention, parts/dataset.py:14-53)."""
+        (the `seq_collate_fn` convention, parts/dataset.py:14-53).  `decoder`: 'greedy' or 'beam'
+        (default: the engine's, i.e. beam search without LM like the reference's `transcribe`)."""
+        kind = decoder or self.decoder_kind
         lens = torch.tensor([len(s) for s in signals], dtype=torch.int64)
         L = int(lens.max())
         w = torch.zeros((len(signals), L), dtype=torch.float32)
         for i, s in enumerate(signals):
             w[i, : len(s)] = torch.as_tensor(np.asarray(s), dtype=torch.float32)
-        ids, n = self.transcribe_host_ids(w.pin_memory(), lens.pin_memory())
-        return asr.ids_to_text(ids, n, self.labels)
+        if kind == "greedy":
+            ids, n = self.transcribe_host_ids(w.pin_memory(), lens.pin_memory())
+            return asr.ids_to_text(ids, n, self.labels)
+        return self.beam_batch_device(w.cuda(non_blocking=True), lens.cuda(non_blocking=True))
 
     def transcribe(self, audio_signal: np.ndarray) -> str:
-        """infer.py:167-171: one utterance -> text."""
+        """infer.py:167-171: one utterance -> text (beam search, no LM, unless the engine was built with
+        decoder='greedy')."""
         return self.transcribe_batch([np.reshape(audio_signal, [-1])])[0]
