@@ -47,6 +47,15 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "source": "fallback"}
 
 
+def load_traffic(mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per subblock_kernel launch from the committed ncu capture
+    (profiles/r1_traffic.json, f16x3, same workload); None for other modes."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if mode != "f16x3" or not os.path.exists(p):
+        return None
+    return json.load(open(p))["traffic_bytes_per_launch"]
+
+
 def algorithmic_counts(jasper, feat_in, T_f, num_classes):
     """Fused-ideal fp32 bytes and flops per utterance: each sub-block reads its
     input once and writes its output once, the residual branch re-reads the block input once."""
@@ -395,7 +404,7 @@ def main():
         "kernel": "subblock_kernel (fused depthwise + tcgen05 1x1 conv + BN + ReLU)" if args.mode != "fp32"
                   else "dw_conv_kernel + pw_gemm_kernel (CUDA-core path)",
         "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (burst copy)",
+        "frac": ach_gbs / peaks["hbm_gbs"], "traffic": load_traffic(args.mode), "peak_source": peaks["source"] + " (burst copy)",
         "launches_per_step": n_sub, "avg_launch_ms": enc_ms_avg / n_sub,
         "algorithmic_bytes_per_launch": enc_bytes / n_sub,
         "tensor": {"achieved": ach_tf, "unit": "TFLOP/s (algorithmic 1x1-conv flops)",

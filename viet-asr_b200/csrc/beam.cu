@@ -114,27 +114,32 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            // candidates in ascending index; if more than MC qualify keep the MC most probable (documented limit)
-            float thr = tok_min;
-            int cnt;
-            for (;;) {
-                cnt = 0;
-                for (int v0 = 0; v0 < V1; v0 += 32) {
-                    const int v = v0 + lane;
-                    const bool f = v < V1 && (s.lp[v] >= thr || v == bi);
-                    cnt += __popc(__ballot_sync(0xffffffffu, f));
-                }
-                if (cnt <= MC) break;
-                // raise the threshold to the smallest qualifying log-prob's successor
-                float mn = INFINITY;
-                for (int v = lane; v < V1; v += 32) { const float x = s.lp[v]; if (x >= thr && v != bi) mn = fminf(mn, x); }
-                for (int o = 16; o >= 1; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                thr = nextafterf(mn, INFINITY);
+            // candidates in ascending index; if more than MC qualify keep the argmax plus the MC-1 most probable
+            // others, ties to the lower index (documented kernel limit; a peaked CTC posterior never reaches it)
+            int cnt = 0;
+            for (int v0 = 0; v0 < V1; v0 += 32) {
+                const int v = v0 + lane;
+                const bool f = v < V1 && (s.lp[v] >= tok_min || v == bi);
+                cnt += __popc(__ballot_sync(0xffffffffu, f));
             }
+            const bool capped = cnt > MC;
+            auto selected = [&](int v) -> bool {
+                if (v >= V1) return false;
+                if (v == bi) return true;
+                const float x = s.lp[v];
+                if (x < tok_min) return false;
+                if (!capped) return true;
+                int rank = 0;                          // qualifying non-argmax symbols ahead of v
+                for (int u = 0; u < V1; ++u) {
+                    const float y = s.lp[u];
+                    if (u != bi && y >= tok_min && (y > x || (y == x && u < v))) ++rank;
+                }
+                return rank < MC - 1;
+            };
             int base = 0;
             for (int v0 = 0; v0 < V1; v0 += 32) {
                 const int v = v0 + lane;
-                const bool f = v < V1 && (s.lp[v] >= thr || v == bi);
+                const bool f = selected(v);
                 const unsigned m = __ballot_sync(0xffffffffu, f);
                 if (f) { const int p = base + __popc(m & ((1u << lane) - 1u)); s.cand[p] = v; s.candp[p] = s.lp[v]; }
                 base += __popc(m);
