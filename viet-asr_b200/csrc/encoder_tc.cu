@@ -439,21 +439,20 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             mbar_wait(acc_full + ab, (ti / nbuf) & 1);
             PROF_ADD(0);
             tcgen05_fence_after();
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(0), ra);
+            // one 32-column slice in registers at a time: with 608 threads the register budget (<= 104) does not
+            // allow a second slice in flight without spilling to local memory, which costs far more than the
+            // exposed tcgen05.ld latency
+            uint32_t ra[32];
 #pragma unroll 1
-            for (int sidx = 0; sidx < nslice; sidx += 2) {     // software-pipelined: the next slice's TMEM load is in flight
+            for (int sidx = 0; sidx < nslice; ++sidx) {
+                tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(sidx), ra);
                 tmem_ld_wait();
-                tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(sidx + 1), rb);
-                finish(ra, slice_col(sidx));
-                tmem_ld_wait();
-                if (sidx + 2 < nslice) tmem_ld_32x32b_x32(tbase + (uint32_t)slice_col(sidx + 2), ra);
-                else {                                         // every TMEM read of this tile has completed
+                if (sidx + 1 == nslice) {                      // every TMEM read of this tile has completed
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + ab);
                 }
-                finish(rb, slice_col(sidx + 1));
+                finish(ra, slice_col(sidx));
             }
             PROF_ADD(1);
         }
