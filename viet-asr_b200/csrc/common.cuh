@@ -64,7 +64,7 @@ struct SubBlock {
     // the inverse pre-scale per output channel, and the TMA descriptors (CUtensorMap, 128 B each)
     void* pw_h = nullptr; void* pw_l = nullptr;
     void* res_h = nullptr; void* res_l = nullptr;
-    float* wscale_inv = nullptr;
+    float wscale_inv_scalar = 1.f;   // 2^-s of the layer's power-of-two weight pre-scale (tcgen05 path)
     float* dw_tc = nullptr;    // [cin/32][kernel][32] depthwise taps for the fused kernel
     alignas(64) unsigned char tm_w_hi[128];
     alignas(64) unsigned char tm_w_lo[128];

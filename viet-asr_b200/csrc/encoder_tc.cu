@@ -173,7 +173,7 @@ constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4) | (0u << 7) | (0u << 10) | (0
 struct Params {
     const float* dw_w;       // [Cin/32][K][32] fp32 depthwise taps (ones for a plain 1x1 conv)
     const float* shift;      // [Cout]
-    const float* wscale_inv; // [Cout] 2^-s of the weight pre-scale
+    float wscale_inv;        // 2^-s of the layer's power-of-two weight pre-scale
     float* out;              // [B, T_out, Cout]
     const int* len_out;      // [B]
     int* tile_counter;       // dynamic tile scheduler (zeroed before the launch)
@@ -204,8 +204,10 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_out, const Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve-up (every operand tile 1024-byte aligned; the launch reserves 1 KiB of slack for this round-up)
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // carve-up: every operand tile must be 1024-byte aligned.  The dynamic window starts right after the driver's
+    // 1 KiB reservation, i.e. aligned; the budget has no slack for a round-up, so fail loudly if that ever changes.
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    unsigned char* smem = smem_raw;
     constexpr int A_SLOT = W_PART * NPART, B_STAGE = PART_BYTES * NPART;   // a_ring = weight slots, b_ring = activation stages
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
@@ -225,6 +227,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* sched_empty = sched_full + SCHED;  // [SCHED] roles -> scheduler
     int* tile_ring = reinterpret_cast<int*>(sched_empty + SCHED);   // [SCHED]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + SCHED);
+    float* ep_shift = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 1024);   // [MAX_CO_CTA] BN shift of this tile's channels
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long pacc[4] = {0ull, 0ull, 0ull, 0ull};
@@ -394,11 +397,19 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const bool issuer = (q == 0 && lane == 0);             // one thread per half-group drives its TMA stores
         unsigned char* stage = epi_stage + half * EPI_STAGE_BYTES;
         const int nslice = p.nN * 4;                           // 32-column slices handled by this half-group
+        const float wsc = p.wscale_inv;
+        int cur_co0 = -1;
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
             if (tile < 0) break;
             int co0, b, t0;
             decode(tile, co0, b, t0);
+            if (co0 != cur_co0) {                              // (re)load the per-channel BN shift of this channel group
+                named_bar_sync(3, NEPI * 32);                  // nobody still reads the previous group's values
+                for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI * 32) ep_shift[i] = __ldg(p.shift + co0 + i);
+                named_bar_sync(3, NEPI * 32);
+                cur_co0 = co0;
+            }
             const int ab = ti % nbuf;
             const int t = t0 + row;
             const bool row_ok = t < p.T_out;
@@ -408,20 +419,19 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
             // +shift (BN), ReLU, length mask on one 32-channel slice held in registers, then out
             auto finish = [&](uint32_t (&rg)[32], int col0) {
-                const float4* sc4 = reinterpret_cast<const float4*>(p.wscale_inv + co0 + col0);
-                const float4* sh4 = reinterpret_cast<const float4*>(p.shift + co0 + col0);
+                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
                 if (p.tma_epi) {
                     if (issuer) bulk_wait_read0();             // previous slice has left the staging buffer
                     named_bar_sync(1 + half, 128);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);     // warp-uniform addresses (broadcast)
+                    const float4 sh = sh4[i];                   // shared-memory broadcast (same address in every lane)
                     float4 v;
-                    v.x = fmaf(__uint_as_float(rg[4 * i + 0]), sc.x, sh.x);
-                    v.y = fmaf(__uint_as_float(rg[4 * i + 1]), sc.y, sh.y);
-                    v.z = fmaf(__uint_as_float(rg[4 * i + 2]), sc.z, sh.z);
-                    v.w = fmaf(__uint_as_float(rg[4 * i + 3]), sc.w, sh.w);
+                    v.x = fmaf(__uint_as_float(rg[4 * i + 0]), wsc, sh.x);
+                    v.y = fmaf(__uint_as_float(rg[4 * i + 1]), wsc, sh.y);
+                    v.z = fmaf(__uint_as_float(rg[4 * i + 2]), wsc, sh.z);
+                    v.w = fmaf(__uint_as_float(rg[4 * i + 3]), wsc, sh.w);
                     if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.tma_epi)                             // 128-byte rows, 16-byte chunks XOR-swizzled by row (SWIZZLE_128B)
@@ -653,7 +663,7 @@ static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_
 static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int* xstages, int* bstages, int* aslots)
 {
     const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
-    const int overhead = 1024 /*barriers*/ + 1024 /*align slack*/ + epi_bytes;
+    const int overhead = 1024 /*barriers*/ + MAX_CO_CTA * 4 /*BN shift*/ + epi_bytes;
     int xs = 2, bs = 2;
     int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
     if (slots > 4 * nN) slots = 4 * nN;
@@ -704,25 +714,25 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
 {
     using namespace tc;
     const int Co = sb.cout, Ci = sb.cin, Cr = sb.has_res ? sb.res_cin : 0;
-    std::vector<float> inv(Co);
     std::vector<__half> mh((size_t)Co * Ci), ml((size_t)Co * Ci), rh((size_t)Co * Cr), rl((size_t)Co * Cr);
-    for (int o = 0; o < Co; ++o) {
-        float mx = 0.f;
-        for (int i = 0; i < Ci; ++i) mx = fmaxf(mx, fabsf(w_main[(size_t)o * Ci + i]));
-        for (int i = 0; i < Cr; ++i) mx = fmaxf(mx, fabsf(w_res[(size_t)o * Cr + i]));
-        int ex = 0;
-        if (mx > 0.f && isfinite(mx)) frexpf(mx, &ex);          // mx = f * 2^ex, f in [0.5, 1)
-        const int s = (mx > 0.f) ? 14 - ex : 0;                   // scaled max in [2^13, 2^14)
-        const float sc = ldexpf(1.f, s);
-        inv[o] = ldexpf(1.f, -s);
-        auto split = [&](float v, __half& h, __half& l) {
-            const float x = v * sc;
-            h = __float2half_rn(x);
-            l = __float2half_rn(x - __half2float(h));
-        };
-        for (int i = 0; i < Ci; ++i) split(w_main[(size_t)o * Ci + i], mh[(size_t)o * Ci + i], ml[(size_t)o * Ci + i]);
-        for (int i = 0; i < Cr; ++i) split(w_res[(size_t)o * Cr + i], rh[(size_t)o * Cr + i], rl[(size_t)o * Cr + i]);
-    }
+    // one power-of-two pre-scale per layer: the largest |w| lands in [2^13, 2^14), so hi and lo = w - hi stay in
+    // fp16's normal range for every weight within 2^17 of the maximum (smaller ones lose lo bits that are below
+    // fp32's own resolution of the dot product anyway)
+    float mx = 0.f;
+    for (size_t i = 0; i < (size_t)Co * Ci; ++i) mx = fmaxf(mx, fabsf(w_main[i]));
+    for (size_t i = 0; i < (size_t)Co * Cr; ++i) mx = fmaxf(mx, fabsf(w_res[i]));
+    int ex = 0;
+    if (mx > 0.f && isfinite(mx)) frexpf(mx, &ex);          // mx = f * 2^ex, f in [0.5, 1)
+    const int sh_bits = (mx > 0.f) ? 14 - ex : 0;
+    const float sc = ldexpf(1.f, sh_bits);
+    sb.wscale_inv_scalar = ldexpf(1.f, -sh_bits);
+    auto split = [&](float v, __half& h, __half& l) {
+        const float x = v * sc;
+        h = __float2half_rn(x);
+        l = __float2half_rn(x - __half2float(h));
+    };
+    for (size_t i = 0; i < (size_t)Co * Ci; ++i) split(w_main[i], mh[i], ml[i]);
+    for (size_t i = 0; i < (size_t)Co * Cr; ++i) split(w_res[i], rh[i], rl[i]);
     auto up = [&](const void* src, size_t bytes, void** dst) -> int {
         void* d = nullptr;
         VASR_CUDA_OK(cudaMalloc(&d, bytes ? bytes : 16));
@@ -732,7 +742,6 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
         return VASR_OK;
     };
     int rc;
-    if ((rc = up(inv.data(), sizeof(float) * Co, (void**)&sb.wscale_inv))) return rc;
     if ((rc = up(mh.data(), sizeof(__half) * mh.size(), &sb.pw_h))) return rc;
     if ((rc = up(ml.data(), sizeof(__half) * ml.size(), &sb.pw_l))) return rc;
     static_assert(sizeof(CUtensorMap) == sizeof(sb.tm_w_hi), "tensor map storage");
@@ -772,7 +781,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
                          sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
     const int npart = split3 ? 2 : 1;
     Params p{};
-    p.dw_w = sb.dw_tc; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv; p.out = y; p.len_out = len_out;
+    p.dw_w = sb.dw_tc; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv_scalar; p.out = y; p.len_out = len_out;
     p.Cin = sb.cin; p.Cres = sb.has_res ? sb.res_cin : 0; p.Cout = sb.cout; p.T_out = T_out;
     p.pad = sb.separable ? sb.pad : 0;
     p.n_main = sb.cin / KC; p.n_res = sb.has_res ? sb.res_cin / KC : 0;
@@ -789,7 +798,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     }
     if (p.aslots < p.nN) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
     const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
-                        (size_t)p.xstages * p.x_stage_bytes + 1024 + 1024 + (p.tma_epi ? 2 * EPI_STAGE_BYTES : 0);
+                        (size_t)p.xstages * p.x_stage_bytes + 1024 + MAX_CO_CTA * 4 + (p.tma_epi ? 2 * EPI_STAGE_BYTES : 0);
     p.b0 = b0;
     // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
     int rc;
