@@ -211,6 +211,29 @@ def test_host_route_equals_device_route(mode):
     assert texts == V.ids_to_text(ids_h, len_h, md["labels"])
 
 
+@pytest.mark.parametrize("mode", ["f16x3"])
+def test_host_route_pipelined_sub_batches(mode):
+    """Batch large enough for the encoder's two sub-batch streams and the copy/compute software pipeline of
+    vasr_transcribe_host: the collapsed ids must equal the device route's bit for bit, repeatedly (regression
+    test for a buffer-geometry race between sub-batches that are several layers apart)."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("en15x5", "rand")
+    eng = _engine(V, md, enc_sd, dec_sd, mode)
+    B, L = 80, 80000
+    g = torch.Generator().manual_seed(77)
+    wave = (0.1 * torch.randn(B, L, generator=g)).clamp_(-1, 1)
+    length = torch.full((B,), L, dtype=torch.int64)
+    length[3] = 61234; wave[3, 61234:] = 0
+    r = eng.forward_device(wave.cuda(), length.cuda())
+    wp, lp_ = wave.pin_memory(), length.pin_memory()
+    for _ in range(4):
+        ids_h, len_h = eng.transcribe_host_ids(wp, lp_)
+        assert torch.equal(len_h, r["out_len"].cpu())
+        assert torch.equal(ids_h, r["out_ids"].cpu())
+    r2 = eng.forward_device(wave.cuda(), length.cuda())
+    assert torch.equal(r2["enc"], r["enc"])
+
+
 def test_neural_factory_infer_like_infer_py():
     """The reference's own wiring (infer.py:99-171) through NeuralModuleFactory.infer, greedy variant."""
     V = _cuda()

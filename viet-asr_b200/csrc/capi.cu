@@ -50,6 +50,10 @@ struct vasr_model {
     std::vector<cudaStream_t> sub_streams;
     std::vector<cudaEvent_t> sub_events;
     cudaEvent_t fork_event = nullptr;
+    // vasr_transcribe_host: H2D of sub-batch i+1 overlaps the front end + encoder of sub-batch i
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t host_start = nullptr;
+    cudaEvent_t copied[8] = {}, ready[8] = {};
     int max_sub = 2;   // measured on B200: 2 sub-batches beat 1 (tail overlap) and 4 (weight re-streaming)
     // scratch of vasr_transcribe_host (grown on demand)
     void* scratch = nullptr; size_t scratch_bytes = 0;
@@ -172,6 +176,9 @@ extern "C" void vasr_model_destroy(vasr_model* m)
     for (cudaStream_t s : m->sub_streams) cudaStreamDestroy(s);
     for (cudaEvent_t e : m->sub_events) cudaEventDestroy(e);
     if (m->fork_event) cudaEventDestroy(m->fork_event);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->host_start) cudaEventDestroy(m->host_start);
+    for (int i = 0; i < 8; ++i) { if (m->copied[i]) cudaEventDestroy(m->copied[i]); if (m->ready[i]) cudaEventDestroy(m->ready[i]); }
     delete m;
 }
 
@@ -322,9 +329,27 @@ extern "C" size_t vasr_encoder_workspace_bytes(const vasr_model* m, int B, int T
     return lens + vasr::TILE_COUNTER_BYTES + 4 * act;
 }
 
-extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
-                                    float* enc, float* enc_len, void* workspace, size_t workspace_bytes,
-                                    void* stream)
+namespace vasr {
+// number of sub-batch streams the tensor path uses for a batch (1 = single stream)
+static int pick_nsub(const vasr_model* m, int B, int T_f)
+{
+    if (m->gemm_mode == VASR_GEMM_FP32_SIMT) return 1;
+    const char* env = getenv("VASR_SUBSTREAMS");
+    int want = env ? atoi(env) : m->max_sub;
+    if (want < 1) want = 1;
+    if (want > 8) want = 8;
+    const int tiles_per_utt = ceil_div(vasr_model_out_frames(m, T_f), 128);
+    while (want > 1 && (B / want) * tiles_per_utt < 64) --want;     // keep every launch >= ~64 tiles
+    return want;
+}
+}  // namespace vasr
+
+// sub_ready: optional [nsub] events; when given, sub-batch s waits for sub_ready[s] only (its features are ready)
+// instead of everything enqueued on `stream` so far, the caller has already zeroed the tile counters and
+// ordered the workspace against earlier work (vasr_transcribe_host).
+static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
+                                float* enc, float* enc_len, void* workspace, size_t workspace_bytes,
+                                void* stream, const cudaEvent_t* sub_ready)
 {
     using namespace vasr;
     VASR_REQUIRE(m && feat && seq_len && enc && workspace, "vasr_encoder_forward: null argument");
@@ -344,22 +369,16 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
     float* DW = (float*)(ws + lens_b + 3 * act);
     int rc;
     VASR_REQUIRE(m->layers.size() * 8 * sizeof(int) <= TILE_COUNTER_BYTES, "too many layers for the tile-counter table");
-    if (m->gemm_mode != VASR_GEMM_FP32_SIMT) VASR_CUDA_OK(cudaMemsetAsync(counters, 0, TILE_COUNTER_BYTES, st));
-    if ((rc = launch_lens((const long long*)seq_len, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
-                          lens, enc_len, st))) return rc;
+    if (!sub_ready) {
+        if (m->gemm_mode != VASR_GEMM_FP32_SIMT) VASR_CUDA_OK(cudaMemsetAsync(counters, 0, TILE_COUNTER_BYTES, st));
+        if ((rc = launch_lens((const long long*)seq_len, B, 0, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
+                              lens, enc_len, st))) return rc;
+    }
 
     // ---- sub-batch plan: contiguous utterance ranges, each on its own stream (tensor path only)
     const bool tc = m->gemm_mode != VASR_GEMM_FP32_SIMT;
-    int nsub = 1;
-    if (tc) {
-        const char* env = getenv("VASR_SUBSTREAMS");
-        int want = env ? atoi(env) : m->max_sub;
-        if (want < 1) want = 1;
-        if (want > 8) want = 8;
-        const int tiles_per_utt = ceil_div(vasr_model_out_frames(m, T_f), 128);
-        while (want > 1 && (B / want) * tiles_per_utt < 64) --want;     // keep every launch >= ~64 tiles
-        nsub = want;
-    }
+    const int nsub = pick_nsub(m, B, T_f);
+    if (sub_ready && nsub < 2) return set_error(VASR_ESTATE, "internal: pipelined host path needs >= 2 sub-batches");
     if (nsub > 1) {
         while ((int)m->sub_streams.size() < nsub) {
             cudaStream_t s2; cudaEvent_t e2;
@@ -368,8 +387,17 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
             m->sub_streams.push_back(s2); m->sub_events.push_back(e2);
         }
         if (!m->fork_event) VASR_CUDA_OK(cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming));
-        VASR_CUDA_OK(cudaEventRecord(m->fork_event, st));
-        for (int s2 = 0; s2 < nsub; ++s2) VASR_CUDA_OK(cudaStreamWaitEvent(m->sub_streams[s2], m->fork_event, 0));
+        if (!sub_ready) {
+            VASR_CUDA_OK(cudaEventRecord(m->fork_event, st));
+            for (int s2 = 0; s2 < nsub; ++s2) VASR_CUDA_OK(cudaStreamWaitEvent(m->sub_streams[s2], m->fork_event, 0));
+        } else {
+            for (int s2 = 0; s2 < nsub; ++s2) {
+                const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
+                VASR_CUDA_OK(cudaStreamWaitEvent(m->sub_streams[s2], sub_ready[s2], 0));
+                if ((rc = launch_lens((const long long*)seq_len, B, b0, b1 - b0, m->n_stage, m->d_st_k, m->d_st_s,
+                                      m->d_st_d, m->d_st_p, lens, enc_len, m->sub_streams[s2]))) return rc;
+            }
+        }
     }
 
     // VASR_GRID_SPLIT=1: each of the nsub concurrent kernels gets 1/nsub of the SMs (kernels of different sub-batches
@@ -394,11 +422,20 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
             const int* len_in = lens + (size_t)sb.len_stage_in * B;
             const int* len_out = lens + (size_t)sb.len_stage_out * B;
             const float* res = sb.has_res ? block_in : nullptr;
+            // Tensor path: every utterance owns a FIXED region of each rotating buffer (batch stride T_f * cmax),
+            // whatever the layer's T and C.  Sub-batches run on their own streams and may be several layers apart
+            // (layers differ in C), so a per-layer [B, T, C] packing would let one sub-batch's output overlap the
+            // rows another sub-batch is still reading.
+            const long long ustride = (long long)T_f * m->cmax;
+            auto bstride_of = [&](const float* ptr, int t, int c) -> long long {
+                return (ptr == feat || ptr == enc) ? (long long)t * c : ustride;
+            };
             if (tc) {
                 for (int s2 = 0; s2 < nsub; ++s2) {
                     const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
                     if (b1 == b0) continue;
-                    if ((rc = launch_subblock_tc(sb, cur, res, out, B, T, T_out, len_in, len_out,
+                    if ((rc = launch_subblock_tc(sb, cur, bstride_of(cur, T, sb.cin), res, bstride_of(block_in, T, sb.res_cin),
+                                                 out, bstride_of(out, T_out, sb.cout), B, T, T_out, len_in, len_out,
                                                  m->gemm_mode == VASR_GEMM_F16X3, b0, b1 - b0,
                                                  counters + li * 8 + s2, grid_limit,
                                                  nsub > 1 ? m->sub_streams[s2] : st))) return rc;
@@ -423,6 +460,13 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
             VASR_CUDA_OK(cudaStreamWaitEvent(st, m->sub_events[s2], 0));
         }
     return VASR_OK;
+}
+
+extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
+                                    float* enc, float* enc_len, void* workspace, size_t workspace_bytes,
+                                    void* stream)
+{
+    return encoder_forward_impl(m, feat, seq_len, B, T_f, enc, enc_len, workspace, workspace_bytes, stream, nullptr);
 }
 
 extern "C" int vasr_decoder_forward(vasr_model* m, const float* enc, int B, int T_e,
@@ -473,18 +517,86 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
         m->scratch_bytes = off;
     }
     char* s = (char*)m->scratch;
-    VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave, wave_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
-    VASR_CUDA_OK(cudaMemcpyAsync(s + o_len, length_host, (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     int rc;
-    if ((rc = vasr_frontend_forward(fe, (const float*)(s + o_wave), (const int64_t*)(s + o_len), B, L,
-                                    (float*)(s + o_feat), (int64_t*)(s + o_seq), st))) return rc;
-    if ((rc = vasr_encoder_forward(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
-                                   (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st))) return rc;
+    const int nsub = pick_nsub(m, B, T_f);
+    cudaStream_t st_user = st;
+    {
+        const char* e8 = getenv("VASR_PIPE_DBG");
+        if (e8 && (atoi(e8) & 8) && nsub >= 2) {
+            static cudaStream_t ms = nullptr; static cudaEvent_t ev_in = nullptr;
+            if (!ms) { VASR_CUDA_OK(cudaStreamCreateWithFlags(&ms, cudaStreamNonBlocking)); VASR_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming)); }
+            VASR_CUDA_OK(cudaEventRecord(ev_in, st_user));
+            VASR_CUDA_OK(cudaStreamWaitEvent(ms, ev_in, 0));
+            st = ms;
+        }
+    }
+    if (nsub < 2) {
+        VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave, wave_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
+        VASR_CUDA_OK(cudaMemcpyAsync(s + o_len, length_host, (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if ((rc = vasr_frontend_forward(fe, (const float*)(s + o_wave), (const int64_t*)(s + o_len), B, L,
+                                        (float*)(s + o_feat), (int64_t*)(s + o_seq), st))) return rc;
+        if ((rc = vasr_encoder_forward(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
+                                       (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st))) return rc;
+    } else {
+        // software pipeline over the encoder's sub-batches: the waveforms of sub-batch i+1 cross PCIe on a copy
+        // stream while sub-batch i runs its front end (on `st`) and its encoder layers (on its sub-stream)
+        if (!m->copy_stream) {
+            VASR_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+            VASR_CUDA_OK(cudaEventCreateWithFlags(&m->host_start, cudaEventDisableTiming));
+            for (int i = 0; i < 8; ++i) {
+                VASR_CUDA_OK(cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming));
+                VASR_CUDA_OK(cudaEventCreateWithFlags(&m->ready[i], cudaEventDisableTiming));
+            }
+        }
+        // tile counters live at the start of the encoder workspace (after the length table)
+        const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
+        VASR_CUDA_OK(cudaMemsetAsync(s + o_ws + lens_b, 0, TILE_COUNTER_BYTES, st));
+        VASR_CUDA_OK(cudaEventRecord(m->host_start, st));                 // scratch is free once earlier work on st is done
+        VASR_CUDA_OK(cudaStreamWaitEvent(m->copy_stream, m->host_start, 0));
+        for (int h = 0; h < nsub; ++h) {
+            const int b0 = (int)((long long)B * h / nsub), b1 = (int)((long long)B * (h + 1) / nsub);
+            VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave + (size_t)b0 * L * sizeof(float), wave_host + (size_t)b0 * L,
+                                         (size_t)(b1 - b0) * L * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+            VASR_CUDA_OK(cudaMemcpyAsync(s + o_len + (size_t)b0 * sizeof(int64_t), length_host + b0,
+                                         (size_t)(b1 - b0) * sizeof(int64_t), cudaMemcpyHostToDevice, m->copy_stream));
+            VASR_CUDA_OK(cudaEventRecord(m->copied[h], m->copy_stream));
+        }
+        const char* pdbg_e = getenv("VASR_PIPE_DBG");
+        const int pdbg = pdbg_e ? atoi(pdbg_e) : 0;
+        if (pdbg & 1) VASR_CUDA_OK(cudaStreamSynchronize(m->copy_stream));
+        for (int h = 0; h < nsub; ++h) {
+            const int b0 = (int)((long long)B * h / nsub), b1 = (int)((long long)B * (h + 1) / nsub);
+            VASR_CUDA_OK(cudaStreamWaitEvent(st, m->copied[h], 0));
+            if ((rc = vasr_frontend_forward(fe, (const float*)(s + o_wave) + (size_t)b0 * L, (const int64_t*)(s + o_len) + b0,
+                                            b1 - b0, L, (float*)(s + o_feat) + (size_t)b0 * T_f * m->feat_in,
+                                            (int64_t*)(s + o_seq) + b0, st))) return rc;
+            VASR_CUDA_OK(cudaEventRecord(m->ready[h], st));
+            if (pdbg & 2) VASR_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        if (pdbg & 4) for (int h = 0; h < nsub; ++h) VASR_CUDA_OK(cudaEventRecord(m->ready[h], st));   // every sub-batch waits for all front ends
+        if ((rc = encoder_forward_impl(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
+                                       (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st, m->ready))) return rc;
+    }
     if ((rc = vasr_decoder_forward(m, (const float*)(s + o_enc), B, T_e, nullptr, (int64_t*)(s + o_ids), st))) return rc;
     if ((rc = vasr_ctc_collapse((const int64_t*)(s + o_ids), B, T_e, m->num_classes - 1, (int32_t*)(s + o_oid),
                                 (int32_t*)(s + o_olen), st))) return rc;
     VASR_CUDA_OK(cudaMemcpyAsync(out_ids_host, s + o_oid, (size_t)B * T_e * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VASR_CUDA_OK(cudaMemcpyAsync(out_len_host, s + o_olen, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VASR_CUDA_OK(cudaStreamSynchronize(st));
+    (void)st_user;
+    if (const char* dump = getenv("VASR_HOST_DUMP")) {       // debugging aid: intermediate tensors of the host route
+        auto dump_buf = [&](const char* name, size_t off_b, size_t bytes) {
+            std::vector<char> h(bytes);
+            cudaMemcpy(h.data(), s + off_b, bytes, cudaMemcpyDeviceToHost);
+            std::string path = std::string(dump) + "/" + name;
+            FILE* f = fopen(path.c_str(), "wb");
+            if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+        };
+        dump_buf("feat.bin", o_feat, (size_t)B * T_f * m->feat_in * sizeof(float));
+        dump_buf("seq.bin", o_seq, (size_t)B * sizeof(int64_t));
+        dump_buf("enc.bin", o_enc, (size_t)B * T_e * C * sizeof(float));
+        dump_buf("ids.bin", o_ids, (size_t)B * T_e * sizeof(int64_t));
+        dump_buf("lens.bin", o_ws, (size_t)(m->n_stage + 1) * B * sizeof(int));
+    }
     return VASR_OK;
 }

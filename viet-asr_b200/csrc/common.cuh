@@ -76,6 +76,7 @@ struct SubBlock {
     const void* tmc_x = nullptr; const void* tmc_r = nullptr; int tmc_B = 0, tmc_T = 0;
     alignas(64) unsigned char tm_y[128];      // output tensor map of the TMA-store epilogue
     const void* tmc_y = nullptr; int tmc_yB = 0, tmc_yT = 0;
+    long long tmc_xs = 0, tmc_rs = 0, tmc_ys = 0;   // batch strides the cached maps were encoded with
 };
 
 }  // namespace vasr

@@ -18,13 +18,13 @@ namespace vasr {
 // The chain only changes at strided layers; every other layer maps len -> len.
 // enc_len (float) = value after the last conv, like the reference's float lengths.
 // ---------------------------------------------------------------------------------------------
-__global__ void lens_kernel(const long long* __restrict__ seq_len, int B, int n_stage,
+__global__ void lens_kernel(const long long* __restrict__ seq_len, int B, int b0, int nb, int n_stage,
                             const int* __restrict__ st_k, const int* __restrict__ st_s,
                             const int* __restrict__ st_d, const int* __restrict__ st_p,
                             int* __restrict__ lens /*[n_stage+1][B]*/, float* __restrict__ enc_len)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const int b = b0 + blockIdx.x * blockDim.x + threadIdx.x;     // utterances [b0, b0 + nb) of a batch of B
+    if (b >= b0 + nb) return;
     long long li = seq_len[b];
     float lf = (float)li;
     lens[b] = (int)li;
@@ -330,10 +330,10 @@ int launch_decoder(const float* enc, const float* W, const float* bias, int Cin,
     return VASR_OK;
 }
 
-int launch_lens(const long long* seq_len, int B, int n_stage, const int* st_k, const int* st_s,
+int launch_lens(const long long* seq_len, int B, int b0, int nb, int n_stage, const int* st_k, const int* st_s,
                 const int* st_d, const int* st_p, int* lens, float* enc_len, cudaStream_t st)
 {
-    lens_kernel<<<ceil_div(B, 128), 128, 0, st>>>(seq_len, B, n_stage, st_k, st_s, st_d, st_p, lens, enc_len);
+    lens_kernel<<<ceil_div(nb, 128), 128, 0, st>>>(seq_len, B, b0, nb, n_stage, st_k, st_s, st_d, st_p, lens, enc_len);
     VASR_LAUNCH_OK("lens_kernel");
     return VASR_OK;
 }

@@ -174,7 +174,8 @@ struct Params {
     const float* dw_w;       // [Cin/32][K][32] fp32 depthwise taps (ones for a plain 1x1 conv)
     const float* shift;      // [Cout]
     float wscale_inv;        // 2^-s of the layer's power-of-two weight pre-scale
-    float* out;              // [B, T_out, Cout]
+    float* out;              // [B, T_out, Cout] with an explicit batch stride (elements)
+    long long out_bstride;
     const int* len_out;      // [B]
     int* tile_counter;       // dynamic tile scheduler (zeroed before the launch)
     int Cin, Cres, Cout, T_out, pad;
@@ -414,7 +415,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const int t = t0 + row;
             const bool row_ok = t < p.T_out;
             const bool live = !(p.mask_tail && t >= p.len_out[b]);
-            float* orow = p.out + ((size_t)b * p.T_out + (row_ok ? t : 0)) * p.Cout + co0;
+            float* orow = p.out + (size_t)b * p.out_bstride + (size_t)(row_ok ? t : 0) * p.Cout + co0;
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
             auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
             // +shift (BN), ReLU, length mask on one 32-channel slice held in registers, then out
@@ -607,18 +608,18 @@ static int encode_tm(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const vo
 }
 
 // activations [B, T, C] fp32 -> 3-D map (C, T, B), box (32, rows, 1), no swizzle, zero OOB fill
-static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, int box_rows)
+static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride, int box_rows)
 {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
+    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)bstride * 4};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 // output [B, T, C] fp32 -> 3-D map (C, T, B), box (32, 128, 1), SWIZZLE_128B (rows beyond T are clipped by the TMA)
-static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C)
+static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride)
 {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4};
+    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)bstride * 4};
     cuuint32_t box[3] = {32, (cuuint32_t)TN, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -768,7 +769,8 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
     return VASR_OK;
 }
 
-int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
+int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const float* res_in, long long r_bstride,
+                       float* y, long long y_bstride, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
                        int* tile_counter, int grid_limit, cudaStream_t st)
 {
@@ -781,7 +783,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
                          sb.cin, sb.cout, sb.kernel, sb.stride, sb.dilation);
     const int npart = split3 ? 2 : 1;
     Params p{};
-    p.dw_w = sb.dw_tc; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv_scalar; p.out = y; p.len_out = len_out;
+    p.dw_w = sb.dw_tc; p.shift = sb.shift; p.wscale_inv = sb.wscale_inv_scalar; p.out = y; p.out_bstride = y_bstride; p.len_out = len_out;
     p.Cin = sb.cin; p.Cres = sb.has_res ? sb.res_cin : 0; p.Cout = sb.cout; p.T_out = T_out;
     p.pad = sb.separable ? sb.pad : 0;
     p.n_main = sb.cin / KC; p.n_res = sb.has_res ? sb.res_cin / KC : 0;
@@ -802,23 +804,23 @@ int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float*
     p.b0 = b0;
     // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
     int rc;
-    if (sb.tmc_x != x || sb.tmc_B != B || sb.tmc_T != T_in) {
-        if ((rc = encode_act((CUtensorMap*)sb.tm_x, x, B, T_in, sb.cin, p.xbox_rows))) return rc;
-        sb.tmc_x = x; sb.tmc_B = B; sb.tmc_T = T_in;
+    if (sb.tmc_x != x || sb.tmc_B != B || sb.tmc_T != T_in || sb.tmc_xs != x_bstride) {
+        if ((rc = encode_act((CUtensorMap*)sb.tm_x, x, B, T_in, sb.cin, x_bstride, p.xbox_rows))) return rc;
+        sb.tmc_x = x; sb.tmc_B = B; sb.tmc_T = T_in; sb.tmc_xs = x_bstride;
         sb.tmc_r = nullptr;
     }
     if (sb.has_res) {
-        if (sb.tmc_r != res_in) {
-            if ((rc = encode_act((CUtensorMap*)sb.tm_r, res_in, B, T_in, sb.res_cin, TN))) return rc;
-            sb.tmc_r = res_in;
+        if (sb.tmc_r != res_in || sb.tmc_rs != r_bstride) {
+            if ((rc = encode_act((CUtensorMap*)sb.tm_r, res_in, B, T_in, sb.res_cin, r_bstride, TN))) return rc;
+            sb.tmc_r = res_in; sb.tmc_rs = r_bstride;
         }
     }
     p.tile_counter = tile_counter;
     p.n_tt = ceil_div(T_out, TN); p.n_utt = nb; p.n_cg = sb.cout / co_cta;
     const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
-    if (sb.tmc_y != y || sb.tmc_yB != B || sb.tmc_yT != T_out) {
-        if ((rc = encode_out((CUtensorMap*)sb.tm_y, y, B, T_out, sb.cout))) return rc;
-        sb.tmc_y = y; sb.tmc_yB = B; sb.tmc_yT = T_out;
+    if (sb.tmc_y != y || sb.tmc_yB != B || sb.tmc_yT != T_out || sb.tmc_ys != y_bstride) {
+        if ((rc = encode_out((CUtensorMap*)sb.tm_y, y, B, T_out, sb.cout, y_bstride))) return rc;
+        sb.tmc_y = y; sb.tmc_yB = B; sb.tmc_yT = T_out; sb.tmc_ys = y_bstride;
     }
     int max_ctas = g_num_sms;                                        // persistent: at most one CTA per SM
     if (grid_limit > 0 && grid_limit < max_ctas) max_ctas = grid_limit;   // concurrent sub-batch kernels share the SMs

@@ -6,7 +6,7 @@
 
 namespace vasr {
 
-int launch_lens(const long long* seq_len, int B, int n_stage, const int* st_k, const int* st_s,
+int launch_lens(const long long* seq_len, int B, int b0, int nb, int n_stage, const int* st_k, const int* st_s,
                 const int* st_d, const int* st_p, int* lens, float* enc_len, cudaStream_t st);
 
 int launch_dw_conv(const float* x, const float* w, float* y, int B, int C, int T_in, int T_out,
@@ -23,7 +23,8 @@ int launch_ctc_collapse(const long long* ids, int B, int T, int blank, int* out_
                         cudaStream_t st);
 
 // tcgen05 fused sub-block (encoder_tc.cu); returns VASR_EINVAL when the shape is not built
-int launch_subblock_tc(SubBlock& sb, const float* x, const float* res_in, float* y, int B, int T_in,
+int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const float* res_in, long long r_bstride,
+                       float* y, long long y_bstride, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
                        int* tile_counter, int grid_limit, cudaStream_t st);
 bool subblock_tc_supported(const SubBlock& sb);
