@@ -384,6 +384,20 @@ def main():
     e2e_value = world * B * CLIP_S / (e2e_ms * 1e-3)
     clocks = sampler.stop() if sampler else None
 
+    # ------------------------------------------------------------ single-utterance latency (the web-app case)
+    lat = None
+    if rank == 0:
+        w1, l1 = synth_batch(1, 777)
+        w1p, l1p = w1.pin_memory(), l1.pin_memory()
+        o1 = torch.empty((1, T_e), dtype=torch.int32).pin_memory(); n1 = torch.empty((1,), dtype=torch.int32).pin_memory()
+        for _ in range(5):
+            eng.transcribe_host_ids(w1p, l1p, o1, n1)
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter(); eng.transcribe_host_ids(w1p, l1p, o1, n1); ts.append((time.perf_counter() - t0) * 1e3)
+        lat = {"batch": 1, "clip_seconds": CLIP_S, "p50_ms": statistics.median(ts), "p90_ms": sorted(ts)[26],
+               "what": "vasr_transcribe_host wall time (H2D + whole path + D2H + sync), greedy"}
+
     # sanity: the device leg and the host leg agree on the transcript of this rank's batch (world==1)
     if world == 1:
         o_ids, o_len = step_device()
@@ -437,6 +451,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "stage_ms": {"encoder": enc_ms_avg, "step": ms_per_step},
+        "latency_b1": lat,
     }
     print(json.dumps(line))
     if world > 1:

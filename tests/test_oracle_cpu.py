@@ -53,3 +53,25 @@ def test_length_chain_is_fractional_then_truncated():
     assert out.shape[-1] == 251 and lens.item() == 250.5
     _, lens2 = O.masked_conv1d(out, lens, torch.zeros(8, 4, 1))
     assert lens2.item() == 250.0
+
+
+def test_beam_oracle_properties():
+    """oracle/beam_oracle.py (restatement of pyctcdecode without LM - parity unpinned): beam width 1 on a peaked
+    posterior equals the greedy collapse; wider beams never score worse; whitespace is normalised."""
+    from oracle import beam_oracle as BO
+    g = load_golden("vi12x1_real_single")
+    import viet_asr_b200 as V
+    labels = V.configs.VI_LABELS
+    lp = torch.from_numpy(g["logits"]).log_softmax(-1)[0].numpy()
+    t1, s1 = BO.beam_search_no_lm(lp, labels, 1)
+    t20, s20 = BO.beam_search_no_lm(lp, labels, 20)
+    greedy = O.ids_to_text(O.ctc_collapse(g["ids"], len(labels)), labels)[0]
+    assert t1 == " ".join(greedy.split())
+    assert s20 >= s1 - 1e-9 and t20 == t1
+    en = V.configs.EN_LABELS
+    T, V1 = 12, len(en) + 1
+    x = np.full((T, V1), -20.0, dtype=np.float32)
+    for t, c in enumerate([0, 0, 8, 28, 9, 0, 28, 0, 20, 28, 28, 28]):      # "  hi  t" with blanks
+        x[t, c] = 0.0
+    x = torch.from_numpy(x).log_softmax(-1).numpy()
+    assert BO.beam_search_no_lm(x, en, 8)[0] == "hi t"

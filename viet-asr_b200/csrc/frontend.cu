@@ -30,7 +30,7 @@ struct vasr_frontend {
 namespace vasr {
 
 // K1: grid (ceil(T_frames / 16), B), block 256.
-// smem: seg[(FE_FRAMES-1)*hop + win] | z[FE_PAIRS][512] float2 | tw[256] float2
+// smem: z[FE_PAIRS][512] float2 | tw[256] float2 | seg[(FE_FRAMES-1)*hop + win]
 __global__ void __launch_bounds__(FE_THREADS)
 stft_mel_kernel(const float* __restrict__ wave, long long L, int T_frames, int T_out,
                 const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -82,30 +82,71 @@ stft_mel_kernel(const float* __restrict__ wave, long long L, int T_frames, int T
     }
     __syncthreads();
 
-    // ---- stage 2: radix-2 DIF FFT, natural order in -> bit-reversed order out -----
+    // ---- stage 2: 512-point complex FFT = three radix-8 Stockham passes (natural order in and out) -----------
+    // 64 threads per transform (one radix-8 butterfly each per pass), 4 transforms at a time; a pass reads its
+    // 8 points (stride 64) into registers, everyone syncs, then writes them back to the same buffer at the
+    // auto-sort positions - 3 shared-memory round trips instead of the 9 of a radix-2 network.
+    {
+        const int ft = tid >> 6;                 // transform within the group of 4
+        const int i = tid & 63;                  // butterfly index
 #pragma unroll 1
-    for (int s = 0; s < 9; ++s) {
-        const int half = (NFFT / 2) >> s;
-        const int grp = tid / half, pos = tid % half;
-        const int i0 = grp * 2 * half + pos, i1 = i0 + half;
-        const float2 w = tw[pos << s];
+        for (int grp = 0; grp < FE_PAIRS / 4; ++grp) {
+            float2* zp = z + (grp * 4 + ft) * NFFT;
 #pragma unroll
-        for (int p = 0; p < FE_PAIRS; ++p) {
-            float2* zp = z + p * NFFT;
-            const float2 a = zp[i0], c = zp[i1];
-            const float dx = a.x - c.x, dy = a.y - c.y;
-            zp[i0] = make_float2(a.x + c.x, a.y + c.y);
-            zp[i1] = make_float2(dx * w.x - dy * w.y, dx * w.y + dy * w.x);
+            for (int pass = 0; pass < 3; ++pass) {
+                const int p = (pass == 0) ? 1 : (pass == 1 ? 8 : 64);
+                const int k = i & (p - 1);
+                const int j = ((i - k) << 3) + k;
+                float2 u[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) u[r] = zp[i + 64 * r];
+                // twiddle u[r] *= exp(-2 pi i * k * r / (8 p)) = tw[(k * r) * (512 / (8 p))]  (table: 256 entries of W512)
+                if (pass > 0) {
+                    const int step = NFFT / (8 * p);                 // 8 for p = 8, 1 for p = 64
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) {
+                        const int e = (k * r * step) & (NFFT - 1);   // exponent of W512, < 512
+                        float2 w = tw[e & (NFFT / 2 - 1)];
+                        if (e >= NFFT / 2) { w.x = -w.x; w.y = -w.y; }   // W^(e) = -W^(e - 256)
+                        const float2 a = u[r];
+                        u[r] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+                    }
+                }
+                // 8-point DFT in registers (three radix-2 levels, decimation in frequency, outputs bit-reversed)
+#define CADD(a, b) make_float2((a).x + (b).x, (a).y + (b).y)
+#define CSUB(a, b) make_float2((a).x - (b).x, (a).y - (b).y)
+#define MULMI(a) make_float2((a).y, -(a).x)                         /* a * (-i) */
+                const float h = 0.70710678118654752440f;
+                float2 a0 = CADD(u[0], u[4]), a4 = CSUB(u[0], u[4]);
+                float2 a1 = CADD(u[1], u[5]), a5 = CSUB(u[1], u[5]);
+                float2 a2 = CADD(u[2], u[6]), a6 = CSUB(u[2], u[6]);
+                float2 a3 = CADD(u[3], u[7]), a7 = CSUB(u[3], u[7]);
+                a5 = make_float2(h * (a5.x + a5.y), h * (a5.y - a5.x));      // * W8^1 = (1 - i)/sqrt2
+                a6 = MULMI(a6);                                               // * W8^2 = -i
+                a7 = make_float2(h * (a7.y - a7.x), -h * (a7.x + a7.y));     // * W8^3 = (-1 - i)/sqrt2
+                float2 b0 = CADD(a0, a2), b2 = CSUB(a0, a2), b1 = CADD(a1, a3), b3 = CSUB(a1, a3);
+                float2 b4 = CADD(a4, a6), b6 = CSUB(a4, a6), b5 = CADD(a5, a7), b7 = CSUB(a5, a7);
+                b3 = MULMI(b3); b7 = MULMI(b7);
+                float2 v[8];
+                v[0] = CADD(b0, b1); v[4] = CSUB(b0, b1); v[2] = CADD(b2, b3); v[6] = CSUB(b2, b3);
+                v[1] = CADD(b4, b5); v[5] = CSUB(b4, b5); v[3] = CADD(b6, b7); v[7] = CSUB(b6, b7);
+#undef CADD
+#undef CSUB
+#undef MULMI
+                __syncthreads();                                     // every butterfly of this pass has read its inputs
+#pragma unroll
+                for (int r = 0; r < 8; ++r) zp[j + r * p] = v[r];
+                __syncthreads();
+            }
         }
-        __syncthreads();
     }
 
     // ---- stage 3: untangle the two spectra, power spectrum re^2 + im^2 -------------
     float pa[FE_PAIRS], pb[FE_PAIRS], pa_ny[FE_PAIRS], pb_ny[FE_PAIRS];
     {
         const int k = tid;                                   // bins 0..255
-        const unsigned rk = __brev((unsigned)k) >> 23;
-        const unsigned rn = __brev((unsigned)((NFFT - k) & (NFFT - 1))) >> 23;
+        const unsigned rk = (unsigned)k;                     // the Stockham passes leave the spectrum in natural order
+        const unsigned rn = (unsigned)((NFFT - k) & (NFFT - 1));
 #pragma unroll
         for (int p = 0; p < FE_PAIRS; ++p) {
             const float2 zk = z[p * NFFT + rk], zn = z[p * NFFT + rn];
@@ -116,7 +157,7 @@ stft_mel_kernel(const float* __restrict__ wave, long long L, int T_frames, int T
             pa_ny[p] = 0.f; pb_ny[p] = 0.f;
         }
         if (tid == 0) {                                      // Nyquist bin 256 (its own mirror)
-            const unsigned r256 = __brev(256u) >> 23;
+            const unsigned r256 = 256u;
 #pragma unroll
             for (int p = 0; p < FE_PAIRS; ++p) {
                 const float2 zk = z[p * NFFT + r256];
