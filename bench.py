@@ -11,7 +11,8 @@ N*256 clips; configs[3]'s 8-GPU run is the same shape with its 1024 clips split 
 One JSON line is printed by rank 0 (see the contract in the task statement):
   value      audio-seconds/s, whole job, inputs already resident in HBM, CUDA-event time, max over ranks
   e2e        same metric through the host-buffer C-ABI call (H2D of the waveforms and D2H of the collapsed
-             ids inside the timed region; at N>1: rank-0 H2D -> NCCL scatter -> compute -> NCCL gather -> D2H)
+             ids inside the timed region; at N>1: per-rank pinned host shard -> H2D -> compute -> NCCL gather of the
+             ids to rank 0 -> D2H; --e2e-scatter: rank-0 H2D -> NCCL scatter -> compute -> NCCL gather -> D2H)
   roofline   dominant kernel family = the fused sub-block kernel (78 launches/step for 15x5), timed live with
              CUDA events around the encoder stage inside the timed region
   cpu_baseline  the oracle (a port of the reference's torch-CPU arithmetic) on this box's host cores,
@@ -259,6 +260,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-scatter", action="store_true", help="N>1: rank-0 H2D of the whole batch + NCCL scatter instead of per-rank host shards")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -349,21 +351,32 @@ def main():
         h2d = B * L * 4 + B * 8
         d2h = B * T_e * 4 + B * 4
     else:
+        # N > 1: one process per GPU, each with its own pinned host shard (the batch is sharded on the host side, so the
+        # waveforms cross each GPU's own PCIe link in parallel); NCCL carries the result gather to rank 0, whose D2H of
+        # the gathered ids closes the step.  `--e2e-scatter` measures the rank-0-H2D + NCCL-scatter variant instead.
         GB = world * B
+        wave_p, len_p = wave_h.pin_memory(), len_h.pin_memory()
+        w_dev = torch.empty((B, L), dtype=torch.float32, device=dev)
+        l_dev = torch.empty((B,), dtype=torch.int64, device=dev)
         if rank == 0:
+            oid_p = torch.empty((GB, T_e), dtype=torch.int32).pin_memory()
+            oln_p = torch.empty((GB,), dtype=torch.int32).pin_memory()
+        if args.e2e_scatter and rank == 0:
             gw = torch.cat([synth_batch(B, 1234 + r)[0] for r in range(world)]).pin_memory()
             gl = torch.full((GB,), L, dtype=torch.int64).pin_memory()
             gw_d = torch.empty((GB, L), dtype=torch.float32, device=dev)
             gl_d = torch.empty((GB,), dtype=torch.int64, device=dev)
-            oid_p = torch.empty((GB, T_e), dtype=torch.int32).pin_memory()
-            oln_p = torch.empty((GB,), dtype=torch.int32).pin_memory()
         else:
             gw_d = gl_d = None
 
         def step_e2e():
-            if rank == 0:
-                gw_d.copy_(gw, non_blocking=True); gl_d.copy_(gl, non_blocking=True)
-            w, ln = D.scatter_batch(gw_d, gl_d, GB, L, dev)
+            if args.e2e_scatter:
+                if rank == 0:
+                    gw_d.copy_(gw, non_blocking=True); gl_d.copy_(gl, non_blocking=True)
+                w, ln = D.scatter_batch(gw_d, gl_d, GB, L, dev)
+            else:
+                w_dev.copy_(wave_p, non_blocking=True); l_dev.copy_(len_p, non_blocking=True)
+                w, ln = w_dev, l_dev
             r = eng.forward_device(w, ln)
             gi, gn = D.gather_results(r["out_ids"], r["out_len"], GB)
             if rank == 0:
@@ -446,7 +459,10 @@ def main():
         "config": {"workload": f"QuartzNet15x5 greedy CTC, batch {B} x 5 s synthetic 16 kHz clips per GPU (BASELINE configs[2])",
                    "global_batch": world * B, "clip_seconds": CLIP_S, "gemm_mode": args.mode, "weights": weights_note,
                    "l2": "per-step working set (82 MB waveforms + 131 MB activations per layer) exceeds the 126 MB L2",
-                   "parallelism": f"dp{world}"},
+                   "parallelism": f"dp{world}",
+                   "e2e_route": ("single C-ABI call vasr_transcribe_host, pinned host buffers" if world == 1 else
+                                 ("rank-0 H2D + NCCL scatter + NCCL gather" if args.e2e_scatter else
+                                  "per-rank pinned host shards, NCCL gather of ids to rank 0"))},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
