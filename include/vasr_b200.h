@@ -152,13 +152,52 @@ int  vasr_ctc_collapse(const int64_t* ids, int B, int T, int blank,
  * log_probs [B, T, V] f32 (all T frames are used, like the reference), blank = V-1 for NeMo vocabularies,
  * space_id = index of ' ' in the vocabulary or -1.  out_ids [B, T] i32 (best text as symbol ids, -1 padded,
  * single spaces, no leading space), out_len [B] i32, out_score [B] f32 (log score, may be NULL).
- * beam_width <= 128; pyctcdecode defaults: token_min_logp = -5, beam_prune_logp = -10.
- * KenLM rescoring is not built (third-party, parity unpinned - DESIGN.md). */
+ * beam_width <= 128; pyctcdecode defaults: token_min_logp = -5, beam_prune_logp = -10. */
 size_t vasr_ctc_beam_workspace_bytes(int B, int T);
 int  vasr_ctc_beam_search(const float* log_probs, int B, int T, int V, int blank, int space_id,
                           int beam_width, float token_min_logp, float beam_prune_logp,
                           void* workspace, size_t workspace_bytes,
                           int32_t* out_ids, int32_t* out_len, float* out_score, void* stream);
+
+/* ---- n-gram language model fused into the beam search ------------------- */
+/* Replaces the kenlm.Model that pyctcdecode.build_ctcdecoder(vocab, kenlm_model_path=lm_path, alpha, beta) opens
+ * (beam_search_decoder.py:82-87; infer.py:184-191: 3-gram-lm.binary, beam 100, alpha 0.5, beta 1.5).
+ * The host decodes the KenLM binary (viet-asr_b200/kenlm_binary.py) into the flat HOST arrays below; vasr_lm_create
+ * copies them to the current device.  Reverse trie: node of n-gram (w1..wn) is reached by wn -> w(n-1) -> ...;
+ * prob/backoff are log10.  *_next[i] .. *_next[i+1] is the child range of node i in the next order's arrays.
+ * vocab_keys/vals: open-addressing table (linear probing, 0 = empty, power-of-two slots) from
+ * vasr_lm_hash_labels(label ids of a word) to its word id; words missing from the table score as <unk> (id 0). */
+typedef struct vasr_lm vasr_lm;
+typedef struct vasr_lm_arrays {
+    int32_t order;                      /* 2..5 */
+    int32_t vocab;                      /* == counts[0] */
+    int32_t bos, eos;                   /* ids of <s>, </s> */
+    const uint64_t* counts;             /* [order] n-grams per order */
+    const float* uni_prob; const float* uni_backoff; const uint32_t* uni_next;      /* [vocab], [vocab], [vocab+1] */
+    const int32_t* mid_word[3]; const float* mid_prob[3]; const float* mid_backoff[3];   /* orders 2..order-1: [counts[k+1]] */
+    const uint32_t* mid_next[3];                                                     /* [counts[k+1] + 1] */
+    const int32_t* long_word; const float* long_prob;                                /* order `order`: [counts[order-1]] */
+    const uint64_t* vocab_keys; const int32_t* vocab_vals; int32_t vocab_slots;
+} vasr_lm_arrays;
+int  vasr_lm_create(const vasr_lm_arrays* host_arrays, vasr_lm** out);
+void vasr_lm_destroy(vasr_lm* lm);
+int  vasr_lm_order(const vasr_lm* lm);
+uint64_t vasr_lm_hash_labels(const int32_t* label_ids, int n);   /* host function: key of a word in vocab_keys */
+/* log10 P(word | ctx) with back-off (kenlm Model.BaseScore) for N queries on the device: ctx [N, 4] i32 oldest ->
+ * newest (first nctx[i] <= order-1 entries used), word [N] i32, out [N] f64 - all device pointers. */
+int  vasr_lm_score_batch(const vasr_lm* lm, const int32_t* ctx, const int32_t* nctx, const int32_t* word,
+                         double* out, int N, void* stream);
+/* Beam search with LM shallow fusion (pyctcdecode decode() with a kenlm model and no unigram list):
+ * candidates ranked by acoustic + sum over words (alpha * ln P_lm(word | history) + beta) + unk_score_offset for a
+ * non-empty partial word (x len/6 beyond 6 characters); out-of-vocabulary words are charged unk_score_offset (log10)
+ * before alpha; a text first completed at the end of the utterance also gets P(</s>).  pyctcdecode default
+ * unk_score_offset = -10.  Labels must be single characters.  out_score = acoustic + LM score of the best text. */
+size_t vasr_ctc_beam_lm_workspace_bytes(int B, int T, int beam_width);
+int  vasr_ctc_beam_search_lm(const float* log_probs, int B, int T, int V, int blank, int space_id,
+                             int beam_width, float token_min_logp, float beam_prune_logp,
+                             const vasr_lm* lm, double alpha, double beta, double unk_score_offset,
+                             void* workspace, size_t workspace_bytes,
+                             int32_t* out_ids, int32_t* out_len, float* out_score, void* stream);
 
 /* ---- whole path, HOST buffers (the reference-facing plugin call) ------- */
 /* wave_host [B, L] f32 and length_host [B] i64 in (pinned or pageable) host memory;

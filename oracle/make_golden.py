@@ -126,7 +126,20 @@ def run_case(name, ref_enc, enc_sd, dec_sd, jasper, pcm16, lens, out_path, label
     print(f"    wrote {out_path} ({os.path.getsize(out_path)/1024:.0f} KiB), min top-2 margin {margin:.4f}")
 
 
+def copy_language_models():
+    """The shipped KenLM binaries are data, not source: copy them next to the checkpoints (git-ignored, they travel to
+    the GPU box with the snapshot) so the LM parity tests can run on real models there."""
+    dst = os.path.join(ROOT, "weights", "lm")
+    os.makedirs(dst, exist_ok=True)
+    for name in ("3-gram-lm.binary", "5-gram-lm.binary"):
+        shutil.copyfile(os.path.join(REF, "models/language_model", name), os.path.join(dst, name))
+        print("copied", name, os.path.getsize(os.path.join(dst, name)), "bytes")
+
+
 def main():
+    copy_language_models()
+    if "--lm-only" in sys.argv:
+        return
     parts = load_ref_parts()
     os.makedirs(os.path.join(ROOT, "tests/golden"), exist_ok=True)
     os.makedirs(os.path.join(ROOT, "weights"), exist_ok=True)

@@ -53,3 +53,50 @@ def model_and_weights(tag, kind):
 
 def pcm_to_wave(pcm16):
     return torch.from_numpy(pcm16.astype(np.float32) / 32768.0)
+
+
+# ----------------------------------------------------------------------------- language-model fixtures
+def tiny_lm_path(order):
+    """tests/golden/tiny_lm_{3,5}gram.binary: small KenLM-format files written by oracle/kenlm_writer.py."""
+    return os.path.join(GOLDEN, f"tiny_lm_{order}gram.binary")
+
+
+def shipped_lm_path(name="3-gram-lm.binary"):
+    """The reference's own KenLM binary, copied to weights/lm by oracle/make_golden.py; skips when absent."""
+    p = os.path.join(WEIGHTS, "lm", name)
+    if not os.path.exists(p):
+        pytest.skip(f"weights/lm/{name} not present (run oracle/make_golden.py --lm-only where /root/reference exists)")
+    return p
+
+
+def spelled_posteriors(sentences, labels, seed, peak=5.0, noise=1.5, confusions=()):
+    """Synthetic CTC log-posteriors [B, T, V+1] that spell `sentences` (blank = last class) with random repeats,
+    blanks and logit noise, so a beam search has real alternatives to weigh.  `confusions`: (utterance, char
+    position, other char) -> that frame group gets a second peak almost as high as the spelled one."""
+    g = np.random.default_rng(seed)
+    lab = {c: i for i, c in enumerate(labels)}
+    blank = len(labels)
+    seqs = []
+    for u, sent in enumerate(sentences):
+        frames = []
+        prev = None
+        for pos, ch in enumerate(sent):
+            c = lab[ch]
+            if prev == c:
+                frames.append((blank, None))
+            alt = [o for (uu, pp, o) in confusions if uu == u and pp == pos]
+            for _ in range(int(g.integers(1, 3))):
+                frames.append((c, lab[alt[0]] if alt else None))
+            for _ in range(int(g.integers(0, 2))):
+                frames.append((blank, None))
+            prev = c
+        seqs.append(frames)
+    T = max(len(f) for f in seqs) + 2
+    x = noise * g.standard_normal((len(sentences), T, blank + 1)).astype(np.float32)
+    for u, frames in enumerate(seqs):
+        for t in range(T):
+            c, alt = frames[t] if t < len(frames) else (blank, None)
+            x[u, t, c] += peak
+            if alt is not None:
+                x[u, t, alt] += peak - 0.3
+    return torch.from_numpy(x).log_softmax(-1)

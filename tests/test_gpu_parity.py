@@ -383,8 +383,8 @@ def test_beam_module_and_engine():
     from oracle import beam_oracle as BO
     md, enc_sd, dec_sd = model_and_weights("vi12x1", "rand")
     eng = _engine(V, md, enc_sd, dec_sd, "fp32")
-    with pytest.raises(NotImplementedError):
-        V.BeamSearchDecoderWithLM(lm_path="3-gram-lm.binary", vocab=md["labels"], beam_width=20, alpha=0.5, beta=1.5, num_cpus=1)
+    with pytest.raises(FileNotFoundError):                                # a missing LM is an error, not a silent no-LM decode
+        V.BeamSearchDecoderWithLM(lm_path="no-such-lm.binary", vocab=md["labels"], beam_width=20, alpha=0.5, beta=1.5, num_cpus=1)
     g = load_golden("vi12x1_rand")
     wave, length = pcm_to_wave(g["pcm16"]), torch.from_numpy(g["lens"])
     r = eng.forward_device(wave.cuda(), length.cuda(), want_log_probs=True)
@@ -394,3 +394,140 @@ def test_beam_module_and_engine():
     assert one == BO.beam_search_no_lm(r["log_probs"][0].cpu().numpy(), md["labels"], 20)[0]
     both = eng.transcribe_batch([w[:n].numpy() for w, n in zip(wave, length)])   # engine default: beam search, no LM
     assert both == [BO.beam_search_no_lm(x.cpu().numpy(), md["labels"], 20)[0] for x in r["log_probs"]]
+
+
+# ----------------------------------------------------------------------------- n-gram LM on the device + LM-fused beam search
+def _lm_queries(m, n_per_kind, seed):
+    """Query mix for the device trie walk: stored n-grams of every order (full match), the same with one context
+    word swapped (back-off), random words, <unk>, short contexts."""
+    rng = np.random.default_rng(seed)
+    V0, order = m.counts[0], m.order
+    nxt = [m.uni_next] + m.mid_next
+    wrd = m.mid_word + [m.long_word]
+    qs = []
+    for n in range(2, order + 1):                               # stored n-gram i of order n -> its word path
+        cnt = m.counts[n - 1]
+        for i in rng.integers(0, cnt, n_per_kind):
+            path, j = [], int(i)
+            for lvl in range(n - 2, -1, -1):                   # walk up: word at this level, then the parent index
+                path.append(int(wrd[lvl][j]))
+                j = int(np.searchsorted(nxt[lvl], j, side="right") - 1)
+            path.append(j)                                      # unigram id = w_n
+            words = path[::-1]                                  # w_n, w_{n-1}, .. -> reversed path is w_n first
+            gram = words[::-1]                                  # oldest -> newest: w_1 .. w_n
+            qs.append((gram[:-1], gram[-1]))
+            swapped = list(gram[:-1]); swapped[int(rng.integers(0, len(swapped)))] = int(rng.integers(0, V0))
+            qs.append((swapped, gram[-1]))
+    for _ in range(n_per_kind):
+        k = int(rng.integers(0, order))
+        qs.append(([int(x) for x in rng.integers(0, V0, k)], int(rng.integers(0, V0))))
+    qs.append(([], 0)); qs.append(([m.bos], 0)); qs.append(([m.bos], m.eos)); qs.append(([0, 0], 0))
+    return qs
+
+
+def _check_device_lm(V, path, labels, n_per_kind):
+    from oracle.kenlm_oracle import KenlmBinary
+    lm = V.NGramLM(path, labels)
+    ora = KenlmBinary(path)
+    from viet_asr_b200.kenlm_binary import KenlmModel
+    qs = _lm_queries(KenlmModel(path), n_per_kind, seed=7)
+    ctx = torch.zeros((len(qs), 4), dtype=torch.int32); nctx = torch.zeros(len(qs), dtype=torch.int32)
+    word = torch.zeros(len(qs), dtype=torch.int32)
+    for i, (c, w) in enumerate(qs):
+        c = c[-(lm.order - 1):]
+        ctx[i, : len(c)] = torch.tensor(c, dtype=torch.int32); nctx[i] = len(c); word[i] = w
+    got = lm.score_batch(ctx.cuda(), nctx.cuda(), word.cuda()).cpu().numpy()
+    want = np.array([ora.score(c, w) for c, w in qs])
+    assert np.array_equal(got, want), np.abs(got - want).max()   # same float32 table values summed in the same order
+    return lm, ora
+
+
+@pytest.mark.parametrize("order", [3, 5])
+def test_device_lm_scores_match_oracle_tiny(order):
+    V = _cuda()
+    from conftest import tiny_lm_path
+    _check_device_lm(V, tiny_lm_path(order), V.configs.EN_LABELS, 300)
+
+
+@pytest.mark.parametrize("name", ["3-gram-lm.binary", "5-gram-lm.binary"])
+def test_device_lm_scores_match_oracle_shipped(name):
+    V = _cuda()
+    from conftest import shipped_lm_path
+    _check_device_lm(V, shipped_lm_path(name), V.configs.VI_LABELS, 400)
+
+
+def _beam_lm_case(V, lp, labels, lm, ora, beam_width, alpha, beta, unk=-10.0):
+    from oracle import beam_oracle as BO
+    ids, n, score = V.ctc_beam_search(lp.cuda(), labels, beam_width, lm=lm, alpha=alpha, beta=beta, unk_score_offset=unk)
+    got = [" ".join(t.split()) for t in V.ids_to_text(ids, n, labels)]
+    for b in range(lp.shape[0]):
+        want, want_score = BO.beam_search_lm(lp[b].numpy(), labels, beam_width, ora, alpha=alpha, beta=beta, unk_score_offset=unk)
+        assert got[b] == want, (b, beam_width, alpha, beta, got[b], want)
+        assert abs(score[b].item() - want_score) < 1e-3 * max(1.0, abs(want_score))
+    return got
+
+
+@pytest.mark.parametrize("order,beam_width,alpha,beta", [(3, 4, 0.5, 1.5), (3, 16, 0.5, 1.5), (5, 16, 0.8, 0.5), (3, 100, 0.5, 1.5),
+                                                         (5, 128, 1.2, 0.0)])
+def test_beam_search_lm_matches_oracle_tiny(order, beam_width, alpha, beta):
+    """LM-fused kernel vs oracle/beam_oracle.beam_search_lm (restatement of pyctcdecode + kenlm, parity UNPINNED
+    against the packages) on synthetic posteriors that spell in- and out-of-vocabulary sentences."""
+    V = _cuda()
+    from conftest import spelled_posteriors, tiny_lm_path
+    from oracle.kenlm_oracle import KenlmBinary
+    labels = V.configs.EN_LABELS
+    path = tiny_lm_path(order)
+    lm, ora = V.NGramLM(path, labels), KenlmBinary(path)
+    sents = ["the cat sat on the mat", "hi there", "a dog and a cat had tea", "zebra quiz the cat", "it's hot", "t",
+             "then she sat at the sea and he had ham too"]
+    for seed, noise in ((1, 0.8), (2, 1.5), (3, 2.2)):
+        lp = spelled_posteriors(sents, labels, seed=seed, noise=noise, confusions=[(0, 5, "x"), (2, 3, "i"), (6, 1, "b")])
+        _beam_lm_case(V, lp, labels, lm, ora, beam_width, alpha, beta)
+
+
+def test_beam_search_lm_degenerates_to_no_lm():
+    V = _cuda()
+    from conftest import spelled_posteriors, tiny_lm_path
+    labels = V.configs.EN_LABELS
+    lm = V.NGramLM(tiny_lm_path(3), labels)
+    lp = spelled_posteriors(["the cat sat on the mat", "hi there", "zebra"], labels, seed=4, noise=1.5).cuda()
+    a = V.ctc_beam_search(lp, labels, 20)
+    b = V.ctc_beam_search(lp, labels, 20, lm=lm, alpha=0.0, beta=0.0, unk_score_offset=0.0)
+    assert V.ids_to_text(a[0], a[1], labels) == V.ids_to_text(b[0], b[1], labels)
+    assert torch.allclose(a[2], b[2], atol=1e-4)
+
+
+@pytest.mark.parametrize("name,beam_width", [("3-gram-lm.binary", 20), ("3-gram-lm.binary", 100), ("5-gram-lm.binary", 100)])
+def test_beam_search_lm_matches_oracle_on_real_speech(name, beam_width):
+    """The reference's default decode (infer.py:184-191: 3-gram LM, beam 100, alpha 0.5, beta 1.5) on the
+    reference-generated posteriors of real Vietnamese speech."""
+    V = _cuda()
+    from conftest import shipped_lm_path
+    from oracle.kenlm_oracle import KenlmBinary
+    labels = V.configs.VI_LABELS
+    path = shipped_lm_path(name)
+    lm, ora = V.NGramLM(path, labels), KenlmBinary(path)
+    for gname in ("vi12x1_real_batch", "vi12x1_real_single"):
+        lp = torch.from_numpy(load_golden(gname)["logits"]).log_softmax(-1)
+        got = _beam_lm_case(V, lp, labels, lm, ora, beam_width, 0.5, 1.5)
+        assert all(len(t) > 0 for t in got)
+
+
+def test_engine_with_language_model():
+    V = _cuda()
+    from conftest import shipped_lm_path
+    from oracle import beam_oracle as BO
+    from oracle.kenlm_oracle import KenlmBinary
+    path = shipped_lm_path("3-gram-lm.binary")
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "real")
+    eng = V.VietASR(model_definition=md, gemm_mode="f16x3", lm_path=path, beam_width=100)
+    eng.load_state_dicts(enc_sd, dec_sd)
+    g = load_golden("vi12x1_real_batch")
+    wave, length = pcm_to_wave(g["pcm16"]), torch.from_numpy(g["lens"])
+    r = eng.forward_device(wave.cuda(), length.cuda(), want_log_probs=True)
+    texts = eng.transcribe_batch([w[:n].numpy() for w, n in zip(wave, length)])
+    ora = KenlmBinary(path)
+    assert texts == [BO.beam_search_lm(x.cpu().numpy(), md["labels"], 100, ora)[0] for x in r["log_probs"]]
+    assert eng.transcribe(wave[2, : length[2]].numpy()) == BO.beam_search_lm(
+        eng.forward_device(wave[2:3, : length[2]].cuda(), length[2:3].cuda(), want_log_probs=True)["log_probs"][0].cpu().numpy(),
+        md["labels"], 100, ora)[0]

@@ -75,3 +75,95 @@ def test_beam_oracle_properties():
         x[t, c] = 0.0
     x = torch.from_numpy(x).log_softmax(-1).numpy()
     assert BO.beam_search_no_lm(x, en, 8)[0] == "hi t"
+
+
+# ----------------------------------------------------------------------------- KenLM binary (oracle + product parser)
+@pytest.mark.parametrize("order", [3, 5])
+def test_kenlm_readers_agree_on_tiny_fixture(order):
+    """oracle/kenlm_oracle.py (scalar bit reads) and viet-asr_b200/kenlm_binary.py (vectorised decode -> flat arrays
+    for the GPU) are independent restatements of the KenLM QUANT_ARRAY_TRIE layout; they must agree on every node."""
+    from conftest import tiny_lm_path
+    from oracle.kenlm_oracle import KenlmBinary
+    from viet_asr_b200.kenlm_binary import KenlmModel
+    a, m = KenlmBinary(tiny_lm_path(order)), KenlmModel(tiny_lm_path(order))
+    assert a.order == m.order == order and a.counts == m.counts and a.words == m.words
+    assert (a.bos, a.eos) == (m.bos, m.eos) and a.words[0] == "<unk>"
+    for w in range(a.counts[0]):
+        p, b, lo, hi = a.unigram(w)
+        assert (m.uni_prob[w], m.uni_backoff[w], m.uni_next[w], m.uni_next[w + 1]) == (np.float32(p), np.float32(b), lo, hi)
+    for k in range(order - 2):
+        for i in range(a.counts[k + 1]):
+            p, b, lo, hi = a.middle(k, i)
+            assert m.mid_word[k][i] == a.middle_word(k, i)
+            assert (m.mid_prob[k][i], m.mid_backoff[k][i], m.mid_next[k][i], m.mid_next[k][i + 1]) == (np.float32(p), np.float32(b), lo, hi)
+    for i in range(a.counts[-1]):
+        assert m.long_word[i] == a.longest_word(i) and m.long_prob[i] == np.float32(a.longest(i))
+
+
+def test_kenlm_oracle_backoff_semantics_on_tiny_fixture():
+    """score() = prob of the longest matching n-gram + back-offs of the unmatched context suffixes."""
+    from conftest import tiny_lm_path
+    from oracle.kenlm_oracle import KenlmBinary
+    from oracle.kenlm_writer import tiny_ngrams
+    lm = KenlmBinary(tiny_lm_path(3))
+    grams = tiny_ngrams(3, 11)
+    tri = [g for g in grams if len(g) == 3][:50]
+    for g in tri:                                              # a stored trigram scores as its own (quantised) prob
+        ids = [lm.index(w) for w in g]
+        found = lm.walk(ids[::-1])
+        assert len(found) == 3 and lm.score(ids[:2], ids[2]) == found[-1][0]
+        assert abs(found[-1][0] - grams[g][0]) < 0.15          # snapped to the nearest of 256 random bins over [-6, 0]
+    # unseen word after a seen bigram context: bigram/unigram prob + the context's back-offs
+    ctx = [lm.index("the"), lm.index("cat")]
+    w = 0                                                       # <unk>: no bigram or trigram ends in it
+    uni = lm.unigram(w)
+    cw = lm.walk(ctx[::-1])
+    assert lm.score(ctx, w) == uni[0] + sum(b for _, b in cw)
+    assert lm.index("zebra") == 0 and lm.score_words(["zebra"]) == lm.score([lm.bos], 0) + lm.score([lm.bos, 0], lm.eos)
+
+
+@pytest.mark.parametrize("name", ["3-gram-lm.binary", "5-gram-lm.binary"])
+def test_kenlm_shipped_model_is_understood(name):
+    """What pins the layout restatement: the reference's own files.  Section sizes add up (checked by the readers),
+    the stored vocabulary hashes are MurmurHash64A of the strings in id order, child ranges are monotone (checked by
+    the product parser) and P(. | context) sums to 1 (to quantisation noise) for contexts of every length."""
+    from conftest import shipped_lm_path
+    from oracle.kenlm_oracle import KenlmBinary
+    from oracle.kenlm_writer import murmur64a
+    from viet_asr_b200.kenlm_binary import KenlmModel
+    path = shipped_lm_path(name)
+    lm = KenlmBinary(path)
+    KenlmModel(path)                                            # raises if its structural checks fail
+    off = (108 + 8 * lm.order + 7) // 8 * 8 + 8
+    h = np.frombuffer(lm.d, dtype="<u8", count=lm.counts[0] - 1, offset=off)
+    assert all(murmur64a(lm.words[i + 1].encode("utf-8")) == int(h[i]) for i in range(0, len(h), 7))
+    rng = np.random.default_rng(0)
+    words = [w for w in ("không", "cần", "phải", "và", "là", "của") if w in lm.word2id]
+    ctxs = [[], [lm.bos]] + [[lm.index(w) for w in words[i:i + n]] for n in (1, 2, 3, 4) for i in (0, 1)]
+    for ctx in ctxs:
+        total = sum(10.0 ** lm.score(ctx, w) for w in range(lm.counts[0]) if w != lm.bos)
+        assert abs(total - 1.0) < 0.03, (ctx, total)
+    assert lm.score_words("không cần phải".split()) > lm.score_words("phải không cần cần".split())
+
+
+def test_beam_lm_oracle_properties():
+    """oracle/beam_oracle.beam_search_lm (restatement of pyctcdecode with a KenLM model - parity unpinned):
+    alpha = beta = unk = 0 reduces to the search without LM; the LM pulls an acoustically ambiguous word towards the
+    vocabulary; the combined score is acoustic + LM."""
+    from conftest import spelled_posteriors, tiny_lm_path
+    from oracle import beam_oracle as BO
+    from oracle.kenlm_oracle import KenlmBinary
+    import viet_asr_b200 as V
+    labels = V.configs.EN_LABELS
+    lm = KenlmBinary(tiny_lm_path(3))
+    lp = spelled_posteriors(["the cat sat on the mat", "hi there"], labels, seed=5, noise=1.0).numpy()
+    for x in lp:
+        t0, s0 = BO.beam_search_no_lm(x, labels, 16)
+        t1, s1 = BO.beam_search_lm(x, labels, 16, lm, alpha=0.0, beta=0.0, unk_score_offset=0.0)
+        assert t0 == t1 and abs(s0 - s1) < 1e-9
+    # 'cat' vs 'cxt' nearly tied acoustically: only the LM (unknown-word penalty) separates them
+    amb = spelled_posteriors(["the cat sat"], labels, seed=9, noise=0.2, confusions=[(0, 5, "x")]).numpy()[0]
+    with_lm = BO.beam_search_lm(amb, labels, 16, lm)[0]
+    assert with_lm == "the cat sat"
+    allb = BO.beam_search_lm(amb, labels, 16, lm, return_all=True)
+    assert allb[0][2] == max(b[2] for b in allb)

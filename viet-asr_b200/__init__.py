@@ -6,11 +6,11 @@ loads this directory, whose on-disk name `viet-asr_b200` is not an identifier).
 from . import _lib, nm, asr, configs          # noqa: F401
 from .asr import (AudioToMelSpectrogramPreprocessor, JasperEncoder, JasperDecoderForCTC,  # noqa: F401
                   GreedyCTCDecoder, BeamSearchDecoderWithLM, post_process_predictions, ctc_collapse,
-                  ctc_beam_search, ids_to_text)
+                  ctc_beam_search, ids_to_text, NGramLM)
 from .nm import (NeuralModuleFactory, DeviceType, NeuralType, NmTensor, DataLayerNM,       # noqa: F401
                  TrainableNM, NonTrainableNM, AudioSignal, LengthsType)
 from .pipeline import VietASR                  # noqa: F401
 
-__all__ = ["AudioToMelSpectrogramPreprocessor", "JasperEncoder", "JasperDecoderForCTC", "GreedyCTCDecoder", "BeamSearchDecoderWithLM", "ctc_beam_search",
+__all__ = ["AudioToMelSpectrogramPreprocessor", "JasperEncoder", "JasperDecoderForCTC", "GreedyCTCDecoder", "BeamSearchDecoderWithLM", "ctc_beam_search", "NGramLM",
            "post_process_predictions", "ctc_collapse", "ids_to_text", "NeuralModuleFactory", "DeviceType",
            "NeuralType", "NmTensor", "DataLayerNM", "TrainableNM", "NonTrainableNM", "VietASR", "configs"]

@@ -29,6 +29,17 @@ class FrontendCfg(C.Structure):
                 ("pad_to", C.c_int32)]
 
 
+class LmArrays(C.Structure):
+    """vasr_lm_arrays (include/vasr_b200.h): host pointers to the decoded KenLM trie."""
+    _fields_ = [("order", C.c_int32), ("vocab", C.c_int32), ("bos", C.c_int32), ("eos", C.c_int32),
+                ("counts", C.c_void_p),
+                ("uni_prob", C.c_void_p), ("uni_backoff", C.c_void_p), ("uni_next", C.c_void_p),
+                ("mid_word", C.c_void_p * 3), ("mid_prob", C.c_void_p * 3), ("mid_backoff", C.c_void_p * 3),
+                ("mid_next", C.c_void_p * 3),
+                ("long_word", C.c_void_p), ("long_prob", C.c_void_p),
+                ("vocab_keys", C.c_void_p), ("vocab_vals", C.c_void_p), ("vocab_slots", C.c_int32)]
+
+
 # every symbol include/vasr_b200.h declares: (restype, argtypes)
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 PROTOTYPES = {
@@ -54,6 +65,14 @@ PROTOTYPES = {
     "vasr_ctc_collapse": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "vasr_ctc_beam_workspace_bytes": (_sz, [_i, _i]),
     "vasr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "vasr_lm_create": (_i, [C.POINTER(LmArrays), C.POINTER(_vp)]),
+    "vasr_lm_destroy": (None, [_vp]),
+    "vasr_lm_order": (_i, [_vp]),
+    "vasr_lm_hash_labels": (C.c_uint64, [_vp, _i]),
+    "vasr_lm_score_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "vasr_ctc_beam_lm_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vasr_ctc_beam_search_lm": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, C.c_double, C.c_double,
+                                     C.c_double, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vasr_transcribe_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
 }
 

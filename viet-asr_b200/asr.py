@@ -479,33 +479,103 @@ class GreedyCTCDecoder(TrainableNM):
 
 
 # --------------------------------------------------------------------------- beam search
+class NGramLM:
+    """Device copy of a KenLM binary for the beam search (what pyctcdecode gets from `kenlm.Model(lm_path)`,
+    beam_search_decoder.py:82-87).  The file is decoded on the host (kenlm_binary.KenlmModel) and uploaded once by
+    `vasr_lm_create`; `vocab` (the acoustic model's labels) fixes the spelling -> word-id table."""
+
+    def __init__(self, lm_path: str, vocab: Sequence[str]):
+        from .kenlm_binary import KenlmModel
+        if not torch.cuda.is_available():
+            raise RuntimeError("NGramLM needs a CUDA device (vasr_b200 has no CPU path)")
+        lib = _lib.load()
+        m = KenlmModel(lm_path)
+
+        def hash_labels(ids):
+            arr = (C.c_int32 * len(ids))(*ids)
+            return int(lib.vasr_lm_hash_labels(arr, len(ids)))
+        table = m.vocabulary_table(list(vocab), hash_labels)
+        keep = []                                           # host arrays must outlive the call
+
+        def ptr(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+        arrs = _lib.LmArrays()
+        arrs.order, arrs.vocab, arrs.bos, arrs.eos = m.order, m.counts[0], m.bos, m.eos
+        arrs.counts = ptr(np.asarray(m.counts), np.uint64)
+        arrs.uni_prob, arrs.uni_backoff = ptr(m.uni_prob, np.float32), ptr(m.uni_backoff, np.float32)
+        arrs.uni_next = ptr(m.uni_next, np.uint32)
+        for k in range(m.order - 2):
+            arrs.mid_word[k] = ptr(m.mid_word[k], np.int32)
+            arrs.mid_prob[k] = ptr(m.mid_prob[k], np.float32)
+            arrs.mid_backoff[k] = ptr(m.mid_backoff[k], np.float32)
+            arrs.mid_next[k] = ptr(m.mid_next[k], np.uint32)
+        arrs.long_word, arrs.long_prob = ptr(m.long_word, np.int32), ptr(m.long_prob, np.float32)
+        arrs.vocab_keys, arrs.vocab_vals = ptr(table["keys"], np.uint64), ptr(table["vals"], np.int32)
+        arrs.vocab_slots = len(table["keys"])
+        h = C.c_void_p()
+        _lib.check(lib.vasr_lm_create(C.byref(arrs), C.byref(h)))
+        self._h = h
+        self.order, self.counts, self.path = m.order, list(m.counts), lm_path
+        self.words, self.word2id, self.bos, self.eos = m.words, m.word2id, m.bos, m.eos
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.load().vasr_lm_destroy(h)
+            self._h = None
+
+    def score_batch(self, ctx: torch.Tensor, nctx: torch.Tensor, word: torch.Tensor) -> torch.Tensor:
+        """log10 P(word | ctx) on the device: ctx [N, 4] i32 (oldest -> newest), nctx [N] i32, word [N] i32 -> [N] f64."""
+        _require_cuda(ctx, "NGramLM.score_batch")
+        ctx = ctx.to(torch.int32).contiguous(); nctx = nctx.to(torch.int32).contiguous(); word = word.to(torch.int32).contiguous()
+        if ctx.dim() != 2 or ctx.shape[1] != 4:
+            raise ValueError("ctx must be [N, 4]")
+        out = torch.empty((ctx.shape[0],), dtype=torch.float64, device=ctx.device)
+        _lib.check(_lib.load().vasr_lm_score_batch(self._h, ctx.data_ptr(), nctx.data_ptr(), word.data_ptr(),
+                                                    out.data_ptr(), ctx.shape[0], _stream_ptr()))
+        return out
+
+
 def ctc_beam_search(log_probs: torch.Tensor, vocab: Sequence[str], beam_width: int,
-                    token_min_logp: float = -5.0, beam_prune_logp: float = -10.0):
-    """Device prefix beam search (no LM): log_probs [B, T, V+1] -> (ids [B, T] i32, len [B] i32, score [B] f32)."""
+                    token_min_logp: float = -5.0, beam_prune_logp: float = -10.0, lm: Optional[NGramLM] = None,
+                    alpha: float = 0.5, beta: float = 1.5, unk_score_offset: float = -10.0):
+    """Device prefix beam search, optionally with n-gram LM fusion: log_probs [B, T, V+1] ->
+    (ids [B, T] i32, len [B] i32, score [B] f32)."""
     _require_cuda(log_probs, "ctc_beam_search")
     lp = log_probs.to(torch.float32).contiguous()
     B, T, V1 = lp.shape
     if V1 != len(vocab) + 1:
         raise ValueError(f"log_probs has {V1} classes but the vocabulary has {len(vocab)} labels (+1 blank)")
     lib = _lib.load()
-    ws = torch.empty((int(lib.vasr_ctc_beam_workspace_bytes(B, T)),), dtype=torch.uint8, device=lp.device)
     ids = torch.empty((B, T), dtype=torch.int32, device=lp.device)
     n = torch.empty((B,), dtype=torch.int32, device=lp.device)
     sc = torch.empty((B,), dtype=torch.float32, device=lp.device)
     space_id = list(vocab).index(" ") if " " in vocab else -1
-    _lib.check(lib.vasr_ctc_beam_search(lp.data_ptr(), B, T, V1, len(vocab), space_id, int(beam_width),
-                                        float(token_min_logp), float(beam_prune_logp), ws.data_ptr(), ws.numel(),
-                                        ids.data_ptr(), n.data_ptr(), sc.data_ptr(), _stream_ptr()))
+    if lm is None:
+        ws = torch.empty((int(lib.vasr_ctc_beam_workspace_bytes(B, T)),), dtype=torch.uint8, device=lp.device)
+        _lib.check(lib.vasr_ctc_beam_search(lp.data_ptr(), B, T, V1, len(vocab), space_id, int(beam_width),
+                                            float(token_min_logp), float(beam_prune_logp), ws.data_ptr(), ws.numel(),
+                                            ids.data_ptr(), n.data_ptr(), sc.data_ptr(), _stream_ptr()))
+    else:
+        nbytes = int(lib.vasr_ctc_beam_lm_workspace_bytes(B, T, int(beam_width)))
+        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=lp.device)
+        _lib.check(lib.vasr_ctc_beam_search_lm(lp.data_ptr(), B, T, V1, len(vocab), space_id, int(beam_width),
+                                               float(token_min_logp), float(beam_prune_logp), lm._h, float(alpha),
+                                               float(beta), float(unk_score_offset), ws.data_ptr(), ws.numel(),
+                                               ids.data_ptr(), n.data_ptr(), sc.data_ptr(), _stream_ptr()))
     return ids, n, sc
 
 
 class BeamSearchDecoderWithLM(NonTrainableNM):
-    """nemo/collections/asr/beam_search_decoder.py:14-102, for `lm_path=None` - the mode infer.py:118-130 falls
-    back to when kenlm is not importable: pyctcdecode's prefix beam search without a language model, here as
-    a batched CUDA kernel (the reference is CPU-only and asserts batch size 1, :96).  `log_probs_length` is
-    ignored like in the reference (:95-101).  KenLM rescoring (`lm_path` set) is NOT built: pyctcdecode and
-    kenlm are un-vendored third-party packages and the shipped LMs are quantised KenLM binaries
-     - asking for it raises NotImplementedError instead of silently decoding without it."""
+    """nemo/collections/asr/beam_search_decoder.py:14-102: pyctcdecode's prefix beam search, here as a batched CUDA
+    kernel (the reference is CPU-only and asserts batch size 1, :96).  `lm_path=None`: no language model (the mode
+    infer.py:118-130 falls back to when kenlm is not importable).  `lm_path=<KenLM binary>`: n-gram shallow fusion
+    with `alpha`, `beta` like `build_ctcdecoder(vocab, kenlm_model_path=lm_path, alpha, beta)` (:82-87); the file is
+    decoded by kenlm_binary.py and searched on the GPU.  `log_probs_length` is ignored like in the reference
+    (:95-101).  pyctcdecode and kenlm are un-vendored third-party packages: parity is against the restatements in
+    oracle/beam_oracle.py and oracle/kenlm_oracle.py (unpinned against the packages)."""
 
     @property
     def input_ports(self):
@@ -521,18 +591,17 @@ class BeamSearchDecoderWithLM(NonTrainableNM):
         super().__init__()
         if self._factory.world_size > 1:
             raise ValueError("BeamSearchDecoderWithLM does not run in distributed mode")   # beam_search_decoder.py:79-80
-        if lm_path is not None:
-            raise NotImplementedError("KenLM rescoring is not built in vasr_b200 (pass lm_path=None for beam search "
-                                      "without a language model)")
         if not 1 <= int(beam_width) <= 128:
             raise ValueError(f"beam_width must be in [1, 128], got {beam_width}")
         self.vocab = list(vocab)
         self.beam_width = int(beam_width)
-        self.alpha, self.beta = alpha, beta          # unused without an LM (kept for the constructor contract)
+        self.alpha, self.beta = float(alpha), float(beta)
         self.num_cpus, self.cutoff_prob, self.cutoff_top_n, self.input_tensor = num_cpus, cutoff_prob, cutoff_top_n, input_tensor
+        self.lm_path = lm_path
+        self.lm = NGramLM(lm_path, self.vocab) if lm_path is not None else None
 
     def decode_batch(self, log_probs) -> List[str]:
-        ids, n, _ = ctc_beam_search(log_probs, self.vocab, self.beam_width)
+        ids, n, _ = ctc_beam_search(log_probs, self.vocab, self.beam_width, lm=self.lm, alpha=self.alpha, beta=self.beta)
         return [" ".join(t.split()) for t in ids_to_text(ids, n, self.vocab)]
 
     def forward(self, log_probs, log_probs_length=None):

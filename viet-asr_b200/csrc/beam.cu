@@ -1,8 +1,18 @@
-// CTC prefix beam search without a language model, batched on the GPU (one CTA per utterance).
-// Replaces BeamSearchDecoderWithLM.forward with lm_path=None (nemo/collections/asr/beam_search_decoder.py:95-102),
-// i.e. pyctcdecode's BeamSearchDecoderCTC.decode without KenLM - the mode infer.py:118-130 falls back to.
-// pyctcdecode is an un-vendored third-party package: the algorithm is restated in oracle/beam_oracle.py
-// (PARITY UNPINNED against the package itself) and this kernel is tested against that restatement.
+// CTC prefix beam search, batched on the GPU (one CTA per utterance), without a language model or with an n-gram
+// LM (KenLM trie uploaded by vasr_lm_create) fused into the search.
+// Replaces BeamSearchDecoderWithLM.forward (nemo/collections/asr/beam_search_decoder.py:95-102), i.e. pyctcdecode's
+// BeamSearchDecoderCTC.decode: with lm_path=None the mode infer.py:118-130 falls back to, with lm_path the default
+// of infer.py:184-191 (3-gram-lm.binary, beam 100, alpha 0.5, beta 1.5).
+// pyctcdecode and kenlm are un-vendored third-party packages: the algorithms are restated in oracle/beam_oracle.py
+// and oracle/kenlm_oracle.py (PARITY UNPINNED against the packages themselves) and this kernel is tested against
+// those restatements.
+//
+// LM fusion (template parameter LM): every beam also carries the LM score of its committed text, the KenLM context
+// (last order-1 word ids), and a rolling hash + length of the partial word.  When ' ' is a candidate symbol the
+// partial word of every beam is looked up in the vocabulary table and scored once per frame (commit_*); candidates
+// are ranked by acoustic + lm(text) + partial-word penalty, beams keep the acoustic score.  pyctcdecode caches
+// lm(text) by text, so a text first seen at the end of the utterance is the only one that gets the </s> term: the
+// per-utterance `seen` hash set (global memory) records every text committed during the search.
 //
 // A beam is a CTC state (prefix, last_char).  Prefixes are identified by a 64-bit rolling hash of their symbol
 // sequence (merging = equal hash + equal last_char); the text is recovered at the end by back-tracing per-frame
@@ -12,6 +22,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include <math.h>
+#include <vector>
 
 namespace vasr {
 namespace beam {
@@ -23,7 +34,7 @@ constexpr int THREADS = 256;
 constexpr unsigned long long H0 = 0x9E3779B97F4A7C15ull;
 constexpr int SYM_NONE = 255, KEY_BLANK = 254, KEY_NONE = 255;
 
-__device__ __forceinline__ unsigned long long mix(unsigned long long h, int c)
+__host__ __device__ __forceinline__ unsigned long long mix(unsigned long long h, int c)
 {
     h ^= (unsigned long long)(c + 1) * 0xD6E8FEB86659FD93ull;
     h *= 0xFF51AFD7ED558CCDull;
@@ -63,13 +74,111 @@ __device__ void bitonic_sort(unsigned long long* k1, unsigned int* k2, int n)
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// n-gram LM in HBM: reverse trie (path w_n -> w_{n-1} -> ...), de-quantised log10 prob / back-off per node
+// (viet-asr_b200/kenlm_binary.py decodes the KenLM file; lm/model.cc GenericModel::FullScore is what lm_score restates)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MAX_ORDER = 5;
+struct DeviceLM {
+    int order, vocab, bos, eos;
+    const float* uni_prob; const float* uni_backoff; const uint32_t* uni_next;
+    const int32_t* mid_word[MAX_ORDER - 2]; const float* mid_prob[MAX_ORDER - 2]; const float* mid_backoff[MAX_ORDER - 2];
+    const uint32_t* mid_next[MAX_ORDER - 2];
+    const int32_t* long_word; const float* long_prob;
+    const unsigned long long* vkeys; const int32_t* vvals; int vmask;
+};
+
+__device__ __forceinline__ int find_word(const int32_t* __restrict__ words, uint32_t lo, uint32_t hi, int w)
+{
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const int x = __ldg(words + mid);
+        if (x < w) lo = mid + 1;
+        else if (x > w) hi = mid;
+        else return (int)mid;
+    }
+    return -1;
+}
+// rev[0..n) = w_n, w_{n-1}, ...: (prob, backoff) of every n-gram suffix that exists; returns how many do (>= 1)
+__device__ int lm_walk(const DeviceLM& lm, const int* rev, int n, float* probs, float* backoffs)
+{
+    const int w0 = rev[0];
+    probs[0] = __ldg(lm.uni_prob + w0); backoffs[0] = __ldg(lm.uni_backoff + w0);
+    uint32_t lo = __ldg(lm.uni_next + w0), hi = __ldg(lm.uni_next + w0 + 1);
+    int L = 1;
+    for (int depth = 1; depth < n && depth < lm.order; ++depth) {
+        const int w = rev[depth];
+        if (depth < lm.order - 1) {
+            const int k = depth - 1;
+            const int i = find_word(lm.mid_word[k], lo, hi, w);
+            if (i < 0) break;
+            probs[depth] = __ldg(lm.mid_prob[k] + i); backoffs[depth] = __ldg(lm.mid_backoff[k] + i);
+            lo = __ldg(lm.mid_next[k] + i); hi = __ldg(lm.mid_next[k] + i + 1);
+        } else {
+            const int i = find_word(lm.long_word, lo, hi, w);
+            if (i < 0) break;
+            probs[depth] = __ldg(lm.long_prob + i); backoffs[depth] = 0.f;
+        }
+        ++L;
+    }
+    return L;
+}
+// log10 P(w | ctx) with back-off; ctx oldest -> newest, nctx <= order - 1
+__device__ double lm_score(const DeviceLM& lm, const int* ctx, int nctx, int w)
+{
+    int rev[MAX_ORDER];
+    float p[MAX_ORDER], bo[MAX_ORDER];
+    rev[0] = w;
+    for (int j = 0; j < nctx; ++j) rev[1 + j] = ctx[nctx - 1 - j];
+    const int L = lm_walk(lm, rev, nctx + 1, p, bo);
+    double prob = (double)p[L - 1];
+    if (L <= nctx) {                                   // charge the back-off of the context n-grams that did not match
+        const int CL = lm_walk(lm, rev + 1, nctx, p, bo);
+        for (int j = L; j <= CL; ++j) prob = __dadd_rn(prob, (double)bo[j - 1]);
+    }
+    return prob;
+}
+__device__ __forceinline__ int vocab_lookup(const DeviceLM& lm, unsigned long long h)
+{
+    int p = (int)(h & (unsigned long long)lm.vmask);
+    while (true) {
+        const unsigned long long k = __ldg(lm.vkeys + p);
+        if (k == h) return __ldg(lm.vvals + p);
+        if (k == 0ull) return -1;
+        p = (p + 1) & lm.vmask;
+    }
+}
+struct LmParams {
+    double alpha, beta, unk, log10_to_ln;
+    unsigned long long* seen;            // [B][seen_cap] hash set of committed texts
+    int seen_cap;                        // power of two
+};
+// lm(text + word) from lm(text): (prev + alpha * raw * ln10) + beta, raw in log10 units (pyctcdecode LanguageModel.score)
+__device__ __forceinline__ double lm_accumulate(const LmParams& q, double prev, double raw)
+{
+    return __dadd_rn(__dadd_rn(prev, __dmul_rn(__dmul_rn(q.alpha, raw), q.log10_to_ln)), q.beta);
+}
+__device__ __forceinline__ double partial_penalty(const LmParams& q, int wl)      // score_partial_token, char trie absent
+{
+    if (wl == 0) return 0.0;
+    return wl > 6 ? __ddiv_rn(__dmul_rn(q.unk, (double)wl), 6.0) : q.unk;
+}
+
 struct Smem {
-    unsigned long long hash[BW_MAX];
+    unsigned long long hash[BW_MAX], fhash[BW_MAX];       // fhash: hash of the text without a trailing space
     double score[BW_MAX];
     unsigned char lastsym[BW_MAX], lastkey[BW_MAX];
-    unsigned long long nhash[BW_MAX];
+    unsigned long long nhash[BW_MAX], nfhash[BW_MAX];
     double nscore[BW_MAX];
     unsigned char nlastsym[BW_MAX], nlastkey[BW_MAX];
+    // LM state per beam (unused without LM)
+    double lmscore[BW_MAX], nlmscore[BW_MAX], commit_lm[BW_MAX];
+    unsigned long long wph[BW_MAX], nwph[BW_MAX];
+    int wplen[BW_MAX], nwplen[BW_MAX];
+    int ctx[BW_MAX][MAX_ORDER - 1], nctx_[BW_MAX][MAX_ORDER - 1], commit_ctx[BW_MAX][MAX_ORDER - 1];
+    int nctx[BW_MAX], nnctx[BW_MAX], commit_nctx[BW_MAX];
+    int has_space;
+    double ucomb[NC_MAX];                // ranking score by unique slot
     float lp[128];
     int cand[MC];
     float candp[MC];
@@ -83,10 +192,12 @@ struct Smem {
     int scan[THREADS / 32];
 };
 
+template <bool LM>
 __global__ void __launch_bounds__(THREADS)
 beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_id, int beam_width,
             float tok_min, float prune, unsigned char* __restrict__ bp_parent, unsigned char* __restrict__ bp_sym,
-            int* __restrict__ out_ids, int* __restrict__ out_len, float* __restrict__ out_score)
+            int* __restrict__ out_ids, int* __restrict__ out_len, float* __restrict__ out_score,
+            const DeviceLM lm, const LmParams q)
 {
     extern __shared__ __align__(16) unsigned char raw[];
     Smem& s = *reinterpret_cast<Smem*>(raw);
@@ -94,12 +205,36 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
     const float* lpb = logp + (size_t)b * T * V1;
     unsigned char* bpp = bp_parent + (size_t)b * T * BW_MAX;
     unsigned char* bps = bp_sym + (size_t)b * T * BW_MAX;
+    unsigned long long* seen = LM ? q.seen + (size_t)b * q.seen_cap : nullptr;
     const float clip_lo = logf(1e-15f);
+    const int nkeep = LM ? lm.order - 1 : 0;               // KenLM context length
 
     if (tid == 0) {
-        s.hash[0] = H0; s.score[0] = 0.0; s.lastsym[0] = SYM_NONE; s.lastkey[0] = KEY_NONE; s.nbeam = 1;
+        s.hash[0] = H0; s.fhash[0] = H0; s.score[0] = 0.0; s.lastsym[0] = SYM_NONE; s.lastkey[0] = KEY_NONE; s.nbeam = 1;
+        if (LM) {                                           // start state: <s> (score_boundary=True)
+            s.lmscore[0] = 0.0; s.wph[0] = H0; s.wplen[0] = 0;
+            s.nctx[0] = nkeep > 0 ? 1 : 0; s.ctx[0][0] = lm.bos;
+        }
     }
     __syncthreads();
+
+    // the word a beam would commit if ' ' came next: id lookup, LM score, new context (one thread per beam)
+    auto commit_word = [&](int i, bool eos) {
+        const int wid_lm = vocab_lookup(lm, s.wph[i]);
+        const int w = wid_lm < 0 ? 0 : wid_lm;             // <unk> = 0
+        double r = lm_score(lm, s.ctx[i], s.nctx[i], w);
+        if (wid_lm < 0) r = __dadd_rn(r, q.unk);            // `word not in kenlm_model`
+        int nc = 0;
+        if (nkeep > 0) {
+            const int have = s.nctx[i];
+            const int drop = have + 1 > nkeep ? have + 1 - nkeep : 0;
+            for (int j = drop; j < have; ++j) s.commit_ctx[i][nc++] = s.ctx[i][j];
+            s.commit_ctx[i][nc++] = w;
+        }
+        s.commit_nctx[i] = nc;
+        if (eos) r = __dadd_rn(r, lm_score(lm, s.commit_ctx[i], nc, lm.eos));
+        s.commit_lm[i] = lm_accumulate(q, s.lmscore[i], r);
+    };
 
     for (int t = 0; t < T; ++t) {
         // ---- 1. frame log-probs (clipped like log(clip(p, 1e-15, 1))) and candidate symbols -------------------
@@ -136,19 +271,33 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
                 }
                 return rank < MC - 1;
             };
-            int base = 0;
+            int base = 0; bool sp = false;
             for (int v0 = 0; v0 < V1; v0 += 32) {
                 const int v = v0 + lane;
                 const bool f = selected(v);
                 const unsigned m = __ballot_sync(0xffffffffu, f);
                 if (f) { const int p = base + __popc(m & ((1u << lane) - 1u)); s.cand[p] = v; s.candp[p] = s.lp[v]; }
+                sp = sp || (__ballot_sync(0xffffffffu, f && v == space_id) != 0u);
                 base += __popc(m);
             }
-            if (lane == 0) s.ncand = base;
+            if (lane == 0) { s.ncand = base; s.has_space = sp ? 1 : 0; }
         }
         __syncthreads();
         const int n = s.nbeam, m = s.ncand, N = n * m;
         int Np = 1; while (Np < N) Np <<= 1;
+
+        // ---- 1b. LM: score the word every beam would commit on ' ' (once per beam and frame) ------------------
+        if (LM && s.has_space && tid < n && s.wplen[tid] > 0) {
+            commit_word(tid, false);
+            // pyctcdecode caches lm(text) for every candidate, kept or not: remember the committed text
+            const unsigned long long h = mix(s.hash[tid], space_id);
+            unsigned int slot = (unsigned int)(h & (unsigned long long)(q.seen_cap - 1));
+            while (true) {
+                const unsigned long long old = atomicCAS(seen + slot, 0ull, h);
+                if (old == 0ull || old == h) break;
+                slot = (slot + 1) & (unsigned int)(q.seen_cap - 1);
+            }
+        }
 
         // ---- 2. expansion, insertion index = cand * n + beam (symbol-major like the reference loop) ------------
         for (int idx = tid; idx < Np; idx += THREADS) {
@@ -187,9 +336,20 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
             if (head) {
                 const int u = off + __popc(bal & ((1u << lane) - 1u));
                 double acc = s.cscore[s.cidx[p]];
-                for (int q = p + 1; q < N && s.ckey[q] == s.ckey[p]; ++q) acc = logaddexp_d(acc, s.cscore[s.cidx[q]]);
+                for (int qq = p + 1; qq < N && s.ckey[qq] == s.ckey[p]; ++qq) acc = logaddexp_d(acc, s.cscore[s.cidx[qq]]);
                 s.uscore[u] = acc;
                 s.urep[u] = s.cidx[p];
+                // ranking score: acoustic, plus lm(text) and the partial-word penalty of the state when an LM is fused
+                double comb = acc;
+                if (LM) {
+                    const unsigned meta = s.cmeta[s.cidx[p]];
+                    const int src = meta & 0xff, app = (meta >> 8) & 0xff;
+                    double lmv; int wl;
+                    if (app == space_id) { lmv = s.commit_lm[src]; wl = 0; }
+                    else { lmv = s.lmscore[src]; wl = s.wplen[src] + (app != SYM_NONE ? 1 : 0); }
+                    comb = __dadd_rn(acc, __dadd_rn(lmv, partial_penalty(q, wl)));
+                }
+                s.ucomb[u] = comb;
             }
             int tot = 0;
             for (int w = 0; w < THREADS / 32; ++w) tot += s.scan[w];
@@ -200,7 +360,7 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
 
         // ---- 4. prune at best + beam_prune_logp, rank by (score desc, first-seen order) ------------------------
         double best = -INFINITY;
-        for (int u = tid; u < U; u += THREADS) best = fmax(best, s.uscore[u]);
+        for (int u = tid; u < U; u += THREADS) best = fmax(best, s.ucomb[u]);
         for (int o = 16; o >= 1; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
         __shared__ double wbest[THREADS / 32];
         if (lane == 0) wbest[wid] = best;
@@ -209,8 +369,8 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
         for (int w = 1; w < THREADS / 32; ++w) best = fmax(best, wbest[w]);
         int Up = 1; while (Up < U) Up <<= 1;
         for (int u = tid; u < Up; u += THREADS) {
-            if (u < U && s.uscore[u] >= best + (double)prune) {
-                s.ckey[u] = ~dkey(s.uscore[u]);            // ascending sort == descending score
+            if (u < U && s.ucomb[u] >= best + (double)prune) {
+                s.ckey[u] = ~dkey(s.ucomb[u]);             // ascending sort == descending score
                 s.cidx[u] = s.urep[u];
             } else { s.ckey[u] = ~0ull; s.cidx[u] = 0xffffffffu; }
         }
@@ -218,9 +378,8 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
         bitonic_sort(s.ckey, s.cidx, Up);
 
         // ---- 5. new beams + back-pointers --------------------------------------------------------------------
-        // cidx now holds representative insertion indices in rank order; the merged score of a representative is
-        // looked up through a second pass (urep is sorted by key order, so search by equality is avoided by storing
-        // the score at the representative's insertion slot)
+        // cidx now holds representative insertion indices in rank order; the merged (acoustic) score of a
+        // representative is stored at the representative's insertion slot
         for (int u = tid; u < U; u += THREADS) s.cscore[s.urep[u]] = s.uscore[u];
         __syncthreads();
         int kept = 0;
@@ -230,10 +389,26 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
                 const unsigned rep = s.cidx[k];
                 const unsigned meta = s.cmeta[rep];
                 const int src = meta & 0xff, app = (meta >> 8) & 0xff;
-                s.nhash[k] = (app == SYM_NONE) ? s.hash[src] : mix(s.hash[src], app);
+                const unsigned long long nh = (app == SYM_NONE) ? s.hash[src] : mix(s.hash[src], app);
+                s.nhash[k] = nh;
+                // text without a trailing space: unchanged by a committed ' ' (the source cannot end in one)
+                s.nfhash[k] = (app == SYM_NONE) ? s.fhash[src] : (app == space_id ? s.hash[src] : nh);
                 s.nscore[k] = s.cscore[rep];
                 s.nlastsym[k] = (unsigned char)((meta >> 16) & 0xff);
                 s.nlastkey[k] = (unsigned char)((meta >> 24) & 0xff);
+                if (LM) {
+                    if (app == space_id) {
+                        s.nlmscore[k] = s.commit_lm[src]; s.nwph[k] = H0; s.nwplen[k] = 0;
+                        s.nnctx[k] = s.commit_nctx[src];
+                        for (int j = 0; j < MAX_ORDER - 1; ++j) s.nctx_[k][j] = s.commit_ctx[src][j];
+                    } else {
+                        s.nlmscore[k] = s.lmscore[src];
+                        s.nwph[k] = (app == SYM_NONE) ? s.wph[src] : mix(s.wph[src], app);
+                        s.nwplen[k] = s.wplen[src] + (app != SYM_NONE ? 1 : 0);
+                        s.nnctx[k] = s.nctx[src];
+                        for (int j = 0; j < MAX_ORDER - 1; ++j) s.nctx_[k][j] = s.ctx[src][j];
+                    }
+                }
                 bpp[(size_t)t * BW_MAX + k] = (unsigned char)src;
                 bps[(size_t)t * BW_MAX + k] = (unsigned char)app;
             }
@@ -248,21 +423,42 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
         __syncthreads();
         if (tid == 0) { int tot = 0; for (int w = 0; w < THREADS / 32; ++w) tot += s.scan[w]; s.nbeam = tot; }
         for (int k = tid; k < BW_MAX; k += THREADS) {
-            s.hash[k] = s.nhash[k]; s.score[k] = s.nscore[k]; s.lastsym[k] = s.nlastsym[k]; s.lastkey[k] = s.nlastkey[k];
+            s.hash[k] = s.nhash[k]; s.fhash[k] = s.nfhash[k]; s.score[k] = s.nscore[k];
+            s.lastsym[k] = s.nlastsym[k]; s.lastkey[k] = s.nlastkey[k];
+            if (LM) {
+                s.lmscore[k] = s.nlmscore[k]; s.wph[k] = s.nwph[k]; s.wplen[k] = s.nwplen[k]; s.nctx[k] = s.nnctx[k];
+                for (int j = 0; j < MAX_ORDER - 1; ++j) s.ctx[k][j] = s.nctx_[k][j];
+            }
         }
         __syncthreads();
     }
 
-    // ---- end of utterance: merge states with equal text (hash), best text wins; back-trace ------------------
+    // ---- end of utterance: the partial word joins the text; states with equal text merge (first-seen order);
+    //      with an LM the text is scored (a text never committed during the search gets the </s> term), the
+    //      best text wins; back-trace -----------------------------------------------------------------------------
+    if (LM && tid < s.nbeam && s.wplen[tid] > 0) {
+        const unsigned long long h = mix(s.hash[tid], space_id);
+        unsigned int slot = (unsigned int)(h & (unsigned long long)(q.seen_cap - 1));
+        bool was_seen = false;
+        while (true) {
+            const unsigned long long k = seen[slot];
+            if (k == h) { was_seen = true; break; }
+            if (k == 0ull) break;
+            slot = (slot + 1) & (unsigned int)(q.seen_cap - 1);
+        }
+        commit_word(tid, !was_seen);
+    }
+    __syncthreads();
     if (tid == 0) {
         const int n = s.nbeam;
         int bi = 0; double bs = -INFINITY;
         for (int i = 0; i < n; ++i) {
             bool first = true;
-            for (int q = 0; q < i; ++q) if (s.hash[q] == s.hash[i]) { first = false; break; }
+            for (int qq = 0; qq < i; ++qq) if (s.fhash[qq] == s.fhash[i]) { first = false; break; }
             if (!first) continue;
             double acc = s.score[i];
-            for (int q = i + 1; q < n; ++q) if (s.hash[q] == s.hash[i]) acc = logaddexp_d(acc, s.score[q]);
+            for (int qq = i + 1; qq < n; ++qq) if (s.fhash[qq] == s.fhash[i]) acc = logaddexp_d(acc, s.score[qq]);
+            if (LM) acc = __dadd_rn(acc, s.wplen[i] > 0 ? s.commit_lm[i] : s.lmscore[i]);
             if (acc > bs) { bs = acc; bi = i; }
         }
         int* oid = out_ids + (size_t)b * T;
@@ -273,14 +469,125 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
             k = bpp[(size_t)t * BW_MAX + k];
         }
         for (int i = 0; i < len / 2; ++i) { const int x = oid[i]; oid[i] = oid[len - 1 - i]; oid[len - 1 - i] = x; }
+        if (len > 0 && oid[len - 1] == space_id) --len;    // whitespace-normalised text: no trailing space
         for (int i = len; i < T; ++i) oid[i] = -1;
         out_len[b] = len;
         if (out_score) out_score[b] = (float)bs;
     }
 }
 
+// batched LM queries (parity tests of the device trie walk): ctx [N, MAX_ORDER-1] oldest -> newest, nctx [N], word [N]
+__global__ void lm_score_kernel(const DeviceLM lm, const int* __restrict__ ctx, const int* __restrict__ nctx,
+                                const int* __restrict__ word, double* __restrict__ out, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int c[MAX_ORDER - 1];
+    for (int j = 0; j < MAX_ORDER - 1; ++j) c[j] = ctx[(size_t)i * (MAX_ORDER - 1) + j];
+    out[i] = lm_score(lm, c, nctx[i], word[i]);
+}
+
 }  // namespace beam
 }  // namespace vasr
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: LM handle + entry points
+// ---------------------------------------------------------------------------------------------------------------------
+struct vasr_lm {
+    vasr::beam::DeviceLM dev{};
+    std::vector<void*> allocs;
+    int device = 0;
+};
+
+namespace {
+template <typename T>
+int upload(vasr_lm* h, const T* src, size_t n, const T** dst)
+{
+    void* p = nullptr;
+    VASR_CUDA_OK(cudaMalloc(&p, n * sizeof(T) + 16));
+    h->allocs.push_back(p);
+    VASR_CUDA_OK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return VASR_OK;
+}
+}  // namespace
+
+extern "C" uint64_t vasr_lm_hash_labels(const int32_t* label_ids, int n)
+{
+    unsigned long long h = vasr::beam::H0;
+    for (int i = 0; i < n; ++i) h = vasr::beam::mix(h, label_ids[i]);
+    return h;
+}
+
+extern "C" void vasr_lm_destroy(vasr_lm* h)
+{
+    if (!h) return;
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+extern "C" int vasr_lm_create(const vasr_lm_arrays* a, vasr_lm** out)
+{
+    using namespace vasr;
+    using namespace vasr::beam;
+    VASR_REQUIRE(a && out, "vasr_lm_create: null argument");
+    VASR_REQUIRE(a->order >= 2 && a->order <= MAX_ORDER, "vasr_lm_create: n-gram order must be in [2, %d] (got %d)", MAX_ORDER, a->order);
+    VASR_REQUIRE(a->counts && a->uni_prob && a->uni_backoff && a->uni_next && a->long_word && a->long_prob,
+                 "vasr_lm_create: null array");
+    VASR_REQUIRE(a->vocab > 0 && (uint64_t)a->vocab == a->counts[0], "vasr_lm_create: vocab does not match counts[0]");
+    VASR_REQUIRE(a->bos >= 0 && a->bos < a->vocab && a->eos >= 0 && a->eos < a->vocab, "vasr_lm_create: <s>/</s> id out of range");
+    VASR_REQUIRE(a->vocab_keys && a->vocab_vals && a->vocab_slots > 0 && (a->vocab_slots & (a->vocab_slots - 1)) == 0,
+                 "vasr_lm_create: vocabulary table must have a power-of-two number of slots");
+    for (int k = 0; k < a->order - 2; ++k)
+        VASR_REQUIRE(a->mid_word[k] && a->mid_prob[k] && a->mid_backoff[k] && a->mid_next[k], "vasr_lm_create: null array for order %d", k + 2);
+    for (int k = 1; k < a->order; ++k)
+        VASR_REQUIRE(a->counts[k] < 0xffffffffull, "vasr_lm_create: more than 2^32 n-grams of order %d", k + 1);
+    vasr_lm* h = new vasr_lm();
+    cudaGetDevice(&h->device);
+    DeviceLM& d = h->dev;
+    d.order = a->order; d.vocab = a->vocab; d.bos = a->bos; d.eos = a->eos; d.vmask = a->vocab_slots - 1;
+    int rc = VASR_OK;
+    auto fail = [&](int code) { vasr_lm_destroy(h); return code; };
+    if ((rc = upload(h, a->uni_prob, (size_t)a->vocab, &d.uni_prob))) return fail(rc);
+    if ((rc = upload(h, a->uni_backoff, (size_t)a->vocab, &d.uni_backoff))) return fail(rc);
+    if ((rc = upload(h, a->uni_next, (size_t)a->vocab + 1, &d.uni_next))) return fail(rc);
+    for (int k = 0; k < a->order - 2; ++k) {
+        const size_t n = (size_t)a->counts[k + 1];
+        if ((rc = upload(h, a->mid_word[k], n, &d.mid_word[k]))) return fail(rc);
+        if ((rc = upload(h, a->mid_prob[k], n, &d.mid_prob[k]))) return fail(rc);
+        if ((rc = upload(h, a->mid_backoff[k], n, &d.mid_backoff[k]))) return fail(rc);
+        if ((rc = upload(h, a->mid_next[k], n + 1, &d.mid_next[k]))) return fail(rc);
+    }
+    const size_t nl = (size_t)a->counts[a->order - 1];
+    if ((rc = upload(h, a->long_word, nl, &d.long_word))) return fail(rc);
+    if ((rc = upload(h, a->long_prob, nl, &d.long_prob))) return fail(rc);
+    const unsigned long long* vk = nullptr;
+    if ((rc = upload(h, (const unsigned long long*)a->vocab_keys, (size_t)a->vocab_slots, &vk))) return fail(rc);
+    d.vkeys = vk;
+    if ((rc = upload(h, a->vocab_vals, (size_t)a->vocab_slots, &d.vvals))) return fail(rc);
+    *out = h;
+    return VASR_OK;
+}
+
+extern "C" int vasr_lm_order(const vasr_lm* h) { return h ? h->dev.order : 0; }
+
+extern "C" int vasr_lm_score_batch(const vasr_lm* h, const int32_t* ctx, const int32_t* nctx, const int32_t* word,
+                                   double* out, int N, void* stream)
+{
+    using namespace vasr;
+    VASR_REQUIRE(h && ctx && nctx && word && out, "vasr_lm_score_batch: null argument");
+    VASR_REQUIRE(N > 0, "vasr_lm_score_batch: N must be positive (got %d)", N);
+    vasr::beam::lm_score_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(h->dev, ctx, nctx, word, out, N);
+    VASR_LAUNCH_OK("lm_score_kernel");
+    return VASR_OK;
+}
+
+static size_t seen_capacity(int T, int beam_width)
+{
+    size_t need = (size_t)2 * T * beam_width, cap = 1024;
+    while (cap < need) cap <<= 1;
+    return cap;
+}
 
 extern "C" size_t vasr_ctc_beam_workspace_bytes(int B, int T)
 {
@@ -288,31 +595,73 @@ extern "C" size_t vasr_ctc_beam_workspace_bytes(int B, int T)
     return (size_t)2 * B * T * vasr::beam::BW_MAX;
 }
 
+extern "C" size_t vasr_ctc_beam_lm_workspace_bytes(int B, int T, int beam_width)
+{
+    if (B <= 0 || T <= 0 || beam_width <= 0) return 0;
+    const size_t bp = ((size_t)2 * B * T * vasr::beam::BW_MAX + 255) / 256 * 256;
+    return bp + (size_t)B * seen_capacity(T, beam_width) * sizeof(unsigned long long);
+}
+
+static int beam_launch(const float* log_probs, int B, int T, int V1, int blank, int space_id, int beam_width,
+                       float token_min_logp, float beam_prune_logp, const vasr_lm* lm, double alpha, double beta,
+                       double unk_score_offset, void* workspace, size_t workspace_bytes,
+                       int32_t* out_ids, int32_t* out_len, float* out_score, void* stream, const char* who)
+{
+    using namespace vasr;
+    using namespace vasr::beam;
+    VASR_REQUIRE(log_probs && workspace && out_ids && out_len, "%s: null argument", who);
+    VASR_REQUIRE(B > 0 && T > 0, "%s: B and T must be positive (got %d, %d)", who, B, T);
+    VASR_REQUIRE(V1 >= 2 && V1 <= 128, "%s: classes (+blank) must be in [2, 128] (got %d)", who, V1);
+    VASR_REQUIRE(beam_width >= 1 && beam_width <= BW_MAX, "%s: beam_width must be in [1, %d] (got %d)", who, BW_MAX, beam_width);
+    VASR_REQUIRE(blank >= 0 && blank < V1, "%s: blank id out of range", who);
+    VASR_REQUIRE(space_id < V1, "%s: space id out of range", who);
+    const size_t need = lm ? vasr_ctc_beam_lm_workspace_bytes(B, T, beam_width) : vasr_ctc_beam_workspace_bytes(B, T);
+    if (workspace_bytes < need)
+        return set_error(VASR_ENOMEM, "%s: workspace %zu < required %zu bytes", who, workspace_bytes, need);
+    static bool attr_set = false;
+    const size_t smem = sizeof(Smem);
+    if (!attr_set) {
+        VASR_CUDA_OK(cudaFuncSetAttribute(beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VASR_CUDA_OK(cudaFuncSetAttribute(beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* bp_parent = (unsigned char*)workspace;
+    unsigned char* bp_sym = bp_parent + (size_t)B * T * BW_MAX;
+    LmParams q{};
+    if (lm) {
+        const size_t bp = ((size_t)2 * B * T * BW_MAX + 255) / 256 * 256;
+        q.alpha = alpha; q.beta = beta; q.unk = unk_score_offset; q.log10_to_ln = 1.0 / log10(M_E);
+        q.seen = (unsigned long long*)((unsigned char*)workspace + bp);
+        q.seen_cap = (int)seen_capacity(T, beam_width);
+        VASR_CUDA_OK(cudaMemsetAsync(q.seen, 0, (size_t)B * q.seen_cap * sizeof(unsigned long long), st));
+        beam_kernel<true><<<B, THREADS, smem, st>>>(log_probs, T, V1, blank, space_id, beam_width, token_min_logp,
+                                                    beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score, lm->dev, q);
+    } else {
+        beam_kernel<false><<<B, THREADS, smem, st>>>(log_probs, T, V1, blank, space_id, beam_width, token_min_logp,
+                                                     beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score, DeviceLM{}, q);
+    }
+    VASR_LAUNCH_OK("beam_kernel");
+    return VASR_OK;
+}
+
 extern "C" int vasr_ctc_beam_search(const float* log_probs, int B, int T, int V1, int blank, int space_id,
                                     int beam_width, float token_min_logp, float beam_prune_logp,
                                     void* workspace, size_t workspace_bytes,
                                     int32_t* out_ids, int32_t* out_len, float* out_score, void* stream)
 {
-    using namespace vasr;
-    using namespace vasr::beam;
-    VASR_REQUIRE(log_probs && workspace && out_ids && out_len, "vasr_ctc_beam_search: null argument");
-    VASR_REQUIRE(B > 0 && T > 0, "vasr_ctc_beam_search: B and T must be positive (got %d, %d)", B, T);
-    VASR_REQUIRE(V1 >= 2 && V1 <= 128, "vasr_ctc_beam_search: classes (+blank) must be in [2, 128] (got %d)", V1);
-    VASR_REQUIRE(beam_width >= 1 && beam_width <= BW_MAX, "vasr_ctc_beam_search: beam_width must be in [1, %d] (got %d)", BW_MAX, beam_width);
-    VASR_REQUIRE(blank >= 0 && blank < V1, "vasr_ctc_beam_search: blank id out of range");
-    const size_t need = vasr_ctc_beam_workspace_bytes(B, T);
-    if (workspace_bytes < need)
-        return set_error(VASR_ENOMEM, "vasr_ctc_beam_search: workspace %zu < required %zu bytes", workspace_bytes, need);
-    static bool attr_set = false;
-    const size_t smem = sizeof(Smem);
-    if (!attr_set) {
-        VASR_CUDA_OK(cudaFuncSetAttribute(beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    unsigned char* bp_parent = (unsigned char*)workspace;
-    unsigned char* bp_sym = bp_parent + (size_t)B * T * BW_MAX;
-    beam_kernel<<<B, THREADS, smem, (cudaStream_t)stream>>>(log_probs, T, V1, blank, space_id, beam_width, token_min_logp,
-                                                            beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score);
-    VASR_LAUNCH_OK("beam_kernel");
-    return VASR_OK;
+    return beam_launch(log_probs, B, T, V1, blank, space_id, beam_width, token_min_logp, beam_prune_logp, nullptr, 0.0, 0.0,
+                       0.0, workspace, workspace_bytes, out_ids, out_len, out_score, stream, "vasr_ctc_beam_search");
+}
+
+extern "C" int vasr_ctc_beam_search_lm(const float* log_probs, int B, int T, int V1, int blank, int space_id,
+                                       int beam_width, float token_min_logp, float beam_prune_logp,
+                                       const vasr_lm* lm, double alpha, double beta, double unk_score_offset,
+                                       void* workspace, size_t workspace_bytes,
+                                       int32_t* out_ids, int32_t* out_len, float* out_score, void* stream)
+{
+    VASR_REQUIRE(lm, "vasr_ctc_beam_search_lm: null language model");
+    return beam_launch(log_probs, B, T, V1, blank, space_id, beam_width, token_min_logp, beam_prune_logp, lm, alpha, beta,
+                       unk_score_offset, workspace, workspace_bytes, out_ids, out_len, out_score, stream,
+                       "vasr_ctc_beam_search_lm");
 }

@@ -14,6 +14,7 @@ accepts batches.  Two execution routes share the same kernels:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -30,9 +31,8 @@ class VietASR:
                  model_definition: Optional[Dict] = None, gemm_mode: str = "f16x3", decoder: str = "beam"):
         if device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("vasr_b200.VietASR runs on a CUDA device only (device='gpu'); there is no CPU path")
-        if lm_path is not None:
-            raise NotImplementedError("KenLM rescoring is not built (SURVEY.md section 8f.1); pass lm_path=None for beam "
-                                      "search without a language model (what infer.py:118-130 falls back to)")
+        if lm_path is not None and not os.path.exists(lm_path):
+            raise FileNotFoundError(f"language model {lm_path!r} does not exist")
         if decoder not in ("beam", "greedy"):
             raise ValueError(f"decoder must be 'beam' or 'greedy', got {decoder!r}")
         self.decoder_kind = decoder
@@ -52,7 +52,7 @@ class VietASR:
         self.decoder = asr.JasperDecoderForCTC(feat_in=md["JasperEncoder"]["jasper"][-1]["filters"],
                                                num_classes=len(self.labels))
         self.greedy = asr.GreedyCTCDecoder()
-        self.beam = asr.BeamSearchDecoderWithLM(lm_path=None, vocab=self.labels, beam_width=beam_width,
+        self.beam = asr.BeamSearchDecoderWithLM(lm_path=lm_path, vocab=self.labels, beam_width=beam_width,
                                                 alpha=lm_alpha, beta=lm_beta, num_cpus=1)
         self.encoder.attach_decoder(self.decoder)
         if encoder_checkpoint:
@@ -107,7 +107,8 @@ class VietASR:
 
     @torch.no_grad()
     def beam_batch_device(self, wave: torch.Tensor, length: torch.Tensor) -> List[str]:
-        """Device tensors -> transcripts through the beam-search decoder (no LM), batched."""
+        """Device tensors -> transcripts through the beam-search decoder (with the n-gram LM when the engine was
+        built with `lm_path`), batched."""
         feat, seq = self.preprocessor.forward_channels_last(wave, length)
         enc, _ = self.encoder.forward_channels_last(feat, seq)
         logp, _ = self.decoder.forward_channels_last(enc, True)
@@ -116,7 +117,8 @@ class VietASR:
     def transcribe_batch(self, signals: Sequence[np.ndarray], decoder: Optional[str] = None) -> List[str]:
         """List of 1-D float waveforms (16 kHz) -> transcripts; zero-pads to the longest
         (the `seq_collate_fn` convention, parts/dataset.py:14-53).  `decoder`: 'greedy' or 'beam'
-        (default: the engine's, i.e. beam search without LM like the reference's `transcribe`)."""
+        (default: the engine's, i.e. beam search - fused with the KenLM model when `lm_path` was given - like the
+        reference's `transcribe`)."""
         kind = decoder or self.decoder_kind
         lens = torch.tensor([len(s) for s in signals], dtype=torch.int64)
         L = int(lens.max())
@@ -129,6 +131,6 @@ class VietASR:
         return self.beam_batch_device(w.cuda(non_blocking=True), lens.cuda(non_blocking=True))
 
     def transcribe(self, audio_signal: np.ndarray) -> str:
-        """infer.py:167-171: one utterance -> text (beam search, no LM, unless the engine was built with
-        decoder='greedy')."""
+        """infer.py:167-171: one utterance -> text (beam search, LM-fused when `lm_path` was given; greedy when the
+        engine was built with decoder='greedy')."""
         return self.transcribe_batch([np.reshape(audio_signal, [-1])])[0]
