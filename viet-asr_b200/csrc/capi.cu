@@ -29,6 +29,8 @@ struct HostTensor { std::vector<int64_t> dims; std::vector<float> data; };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr size_t TILE_COUNTER_BYTES = 8192;   // one int per (layer, sub-batch) launch of the persistent kernels
+// tile counters + the (layer, utterance) completion counters of the multi-layer segment kernels; zeroed per forward
+static inline size_t sync_region_bytes(size_t n_layers, int B) { return TILE_COUNTER_BYTES + align_up(n_layers * (size_t)B * sizeof(int), 256); }
 
 }  // namespace vasr
 
@@ -326,7 +328,7 @@ extern "C" size_t vasr_encoder_workspace_bytes(const vasr_model* m, int B, int T
     // (T never grows along the stack), + the length table
     const size_t act = vasr::align_up((size_t)B * T_f * m->cmax * sizeof(float), 256);
     const size_t lens = vasr::align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
-    return lens + vasr::TILE_COUNTER_BYTES + 4 * act;
+    return lens + vasr::sync_region_bytes(m->layers.size(), B) + 4 * act;
 }
 
 namespace vasr {
@@ -362,15 +364,17 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     int* lens = (int*)ws;
-    const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256) + TILE_COUNTER_BYTES;
-    int* counters = (int*)(ws + lens_b - TILE_COUNTER_BYTES);
+    const size_t sync_b = sync_region_bytes(m->layers.size(), B);
+    const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256) + sync_b;
+    int* counters = (int*)(ws + lens_b - sync_b);
+    int* done = (int*)(ws + lens_b - sync_b + TILE_COUNTER_BYTES);   // [layer][B] completion counters (segment kernels)
     const size_t act = align_up((size_t)B * T_f * m->cmax * sizeof(float), 256);
     float* P[3] = {(float*)(ws + lens_b), (float*)(ws + lens_b + act), (float*)(ws + lens_b + 2 * act)};
     float* DW = (float*)(ws + lens_b + 3 * act);
     int rc;
     VASR_REQUIRE(m->layers.size() * 8 * sizeof(int) <= TILE_COUNTER_BYTES, "too many layers for the tile-counter table");
     if (!sub_ready) {
-        if (m->gemm_mode != VASR_GEMM_FP32_SIMT) VASR_CUDA_OK(cudaMemsetAsync(counters, 0, TILE_COUNTER_BYTES, st));
+        if (m->gemm_mode != VASR_GEMM_FP32_SIMT) VASR_CUDA_OK(cudaMemsetAsync(counters, 0, sync_b, st));
         if ((rc = launch_lens((const long long*)seq_len, B, 0, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
                               lens, enc_len, st))) return rc;
     }
@@ -404,55 +408,95 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
     // then run side by side, out of phase, instead of back to back)
     int grid_limit = 0;
     if (nsub > 1) { const char* e = getenv("VASR_GRID_SPLIT"); if (e && atoi(e) > 0) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); grid_limit = sms / nsub; } }
-    const float* cur = feat;
-    const float* block_in = feat;
-    int T = T_f;
-    size_t li = 0;
-    for (size_t b = 0; b < m->blocks.size(); ++b) {
-        const vasr_block_cfg& c = m->blocks[b];
-        block_in = cur;
-        for (int r = 0; r < c.repeat; ++r, ++li) {
-            SubBlock& sb = m->layers[li];
-            const int T_out = (T + 2 * sb.pad - sb.dilation * (sb.kernel - 1) - 1) / sb.stride + 1;
-            float* out = nullptr;
-            if (sb.final_layer) out = enc;
-            else
-                for (int q = 0; q < 3; ++q)
-                    if (P[q] != cur && P[q] != block_in) { out = P[q]; break; }
-            const int* len_in = lens + (size_t)sb.len_stage_in * B;
-            const int* len_out = lens + (size_t)sb.len_stage_out * B;
-            const float* res = sb.has_res ? block_in : nullptr;
-            // Tensor path: every utterance owns a FIXED region of each rotating buffer (batch stride T_f * cmax),
-            // whatever the layer's T and C.  Sub-batches run on their own streams and may be several layers apart
-            // (layers differ in C), so a per-layer [B, T, C] packing would let one sub-batch's output overlap the
-            // rows another sub-batch is still reading.
-            const long long ustride = (long long)T_f * m->cmax;
-            auto bstride_of = [&](const float* ptr, int t, int c) -> long long {
-                return (ptr == feat || ptr == enc) ? (long long)t * c : ustride;
-            };
-            if (tc) {
-                for (int s2 = 0; s2 < nsub; ++s2) {
-                    const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
-                    if (b1 == b0) continue;
-                    if ((rc = launch_subblock_tc(sb, cur, bstride_of(cur, T, sb.cin), res, bstride_of(block_in, T, sb.res_cin),
-                                                 out, bstride_of(out, T_out, sb.cout), B, T, T_out, len_in, len_out,
-                                                 m->gemm_mode == VASR_GEMM_F16X3, b0, b1 - b0,
-                                                 counters + li * 8 + s2, grid_limit,
-                                                 nsub > 1 ? m->sub_streams[s2] : st))) return rc;
-                }
-            } else {
-                const float* gin = cur;
-                if (sb.separable) {
-                    if ((rc = launch_dw_conv(cur, sb.dw_w, DW, B, sb.cin, T, T_out, sb.kernel, sb.stride,
-                                             sb.dilation, sb.pad, len_in, len_out, st))) return rc;
-                    gin = DW;
-                }
-                if ((rc = launch_pw_gemm(gin, sb.pw_w, sb.cin, res, sb.res_w, sb.res_cin, sb.shift, out, B, T_out,
-                                         sb.cout, len_out, sb.relu ? 1 : 0, sb.final_layer ? 0 : 1, st))) return rc;
+    // ---- plan: buffers and shapes of every layer (3 rotating buffers; the output never aliases the layer's input
+    // or the block input).  Tensor path: every utterance owns a FIXED region of each rotating buffer (batch stride
+    // T_f * cmax), whatever the layer's T and C.  Sub-batches run on their own streams and may be several layers
+    // apart (layers differ in C), so a per-layer [B, T, C] packing would let one sub-batch's output overlap the rows
+    // another sub-batch is still reading.  The same invariant makes the multi-layer segment kernels safe: a tile only
+    // ever touches its own utterance's regions, and it starts after every tile of the previous layer of that utterance.
+    struct Plan { size_t li; const float* cur; const float* res; float* out; int T, T_out; long long xs, rs, ys; const int* len_in; const int* len_out; };
+    std::vector<Plan> plan;
+    {
+        const float* cur = feat;
+        const float* block_in = feat;
+        int T = T_f;
+        size_t li = 0;
+        const long long ustride = (long long)T_f * m->cmax;
+        for (size_t b = 0; b < m->blocks.size(); ++b) {
+            const vasr_block_cfg& c = m->blocks[b];
+            block_in = cur;
+            for (int r = 0; r < c.repeat; ++r, ++li) {
+                SubBlock& sb = m->layers[li];
+                const int T_out = (T + 2 * sb.pad - sb.dilation * (sb.kernel - 1) - 1) / sb.stride + 1;
+                float* out = nullptr;
+                if (sb.final_layer) out = enc;
+                else
+                    for (int q = 0; q < 3; ++q)
+                        if (P[q] != cur && P[q] != block_in) { out = P[q]; break; }
+                auto bstride_of = [&](const float* ptr, int t, int ch) -> long long {
+                    return (ptr == feat || ptr == enc) ? (long long)t * ch : ustride;
+                };
+                Plan pl;
+                pl.li = li; pl.cur = cur; pl.res = sb.has_res ? block_in : nullptr; pl.out = out; pl.T = T; pl.T_out = T_out;
+                pl.xs = bstride_of(cur, T, sb.cin); pl.rs = bstride_of(block_in, T, sb.res_cin); pl.ys = bstride_of(out, T_out, sb.cout);
+                pl.len_in = lens + (size_t)sb.len_stage_in * B; pl.len_out = lens + (size_t)sb.len_stage_out * B;
+                plan.push_back(pl);
+                cur = out;
+                T = T_out;
             }
-            cur = out;
-            T = T_out;
         }
+    }
+    static int mega = -1;
+    if (mega < 0) { const char* e = getenv("VASR_TC_MEGA"); mega = (e && atoi(e) == 0) ? 0 : 1; }
+    const int split3 = m->gemm_mode == VASR_GEMM_F16X3;
+    for (size_t i = 0; i < plan.size();) {
+        // longest run of layers that one segment kernel can execute
+        size_t j = i;
+        std::vector<SegLayer> seg;
+        if (tc && mega) {
+            while (j < plan.size()) {
+                const Plan& pl = plan[j];
+                SubBlock& sb = m->layers[pl.li];
+                if (!segment_tc_layer_ok(sb) || pl.T != pl.T_out) break;
+                if (!seg.empty() && (sb.cout != seg[0].sb->cout || pl.T != plan[i].T)) break;
+                seg.push_back(SegLayer{&sb, pl.cur, pl.xs, pl.res, pl.rs, pl.out, pl.ys, pl.len_out});
+                if (!segment_tc_ok(seg.data(), (int)seg.size(), split3) && seg.size() >= 2) { seg.pop_back(); break; }
+                ++j;
+            }
+            if (seg.size() < 2 || !segment_tc_ok(seg.data(), (int)seg.size(), split3)) { seg.clear(); j = i; }
+        }
+        if (!seg.empty()) {
+            for (int s2 = 0; s2 < nsub; ++s2) {
+                const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
+                if (b1 == b0) continue;
+                if ((rc = launch_segment_tc(seg.data(), (int)seg.size(), B, plan[i].T, split3, b0, b1 - b0,
+                                            counters + plan[i].li * 8 + s2, done + plan[i].li * (size_t)B, B, grid_limit,
+                                            nsub > 1 ? m->sub_streams[s2] : st))) return rc;
+            }
+            i = j;
+            continue;
+        }
+        const Plan& pl = plan[i];
+        SubBlock& sb = m->layers[pl.li];
+        if (tc) {
+            for (int s2 = 0; s2 < nsub; ++s2) {
+                const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
+                if (b1 == b0) continue;
+                if ((rc = launch_subblock_tc(sb, pl.cur, pl.xs, pl.res, pl.rs, pl.out, pl.ys, B, pl.T, pl.T_out, pl.len_in, pl.len_out,
+                                             split3, b0, b1 - b0, counters + pl.li * 8 + s2, grid_limit,
+                                             nsub > 1 ? m->sub_streams[s2] : st))) return rc;
+            }
+        } else {
+            const float* gin = pl.cur;
+            if (sb.separable) {
+                if ((rc = launch_dw_conv(pl.cur, sb.dw_w, DW, B, sb.cin, pl.T, pl.T_out, sb.kernel, sb.stride,
+                                         sb.dilation, sb.pad, pl.len_in, pl.len_out, st))) return rc;
+                gin = DW;
+            }
+            if ((rc = launch_pw_gemm(gin, sb.pw_w, sb.cin, pl.res, sb.res_w, sb.res_cin, sb.shift, pl.out, B, pl.T_out,
+                                     sb.cout, pl.len_out, sb.relu ? 1 : 0, sb.final_layer ? 0 : 1, st))) return rc;
+        }
+        ++i;
     }
     if (nsub > 1)
         for (int s2 = 0; s2 < nsub; ++s2) {
@@ -550,7 +594,7 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
         }
         // tile counters live at the start of the encoder workspace (after the length table)
         const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
-        VASR_CUDA_OK(cudaMemsetAsync(s + o_ws + lens_b, 0, TILE_COUNTER_BYTES, st));
+        VASR_CUDA_OK(cudaMemsetAsync(s + o_ws + lens_b, 0, sync_region_bytes(m->layers.size(), B), st));
         VASR_CUDA_OK(cudaEventRecord(m->host_start, st));                 // scratch is free once earlier work on st is done
         VASR_CUDA_OK(cudaStreamWaitEvent(m->copy_stream, m->host_start, 0));
         for (int h = 0; h < nsub; ++h) {

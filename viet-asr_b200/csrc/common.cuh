@@ -77,6 +77,7 @@ struct SubBlock {
     alignas(64) unsigned char tm_y[128];      // output tensor map of the TMA-store epilogue
     const void* tmc_y = nullptr; int tmc_yB = 0, tmc_yT = 0;
     long long tmc_xs = 0, tmc_rs = 0, tmc_ys = 0;   // batch strides the cached maps were encoded with
+    unsigned long long uid = 0;                      // unique per prepared layer (keys the segment descriptor cache)
 };
 
 }  // namespace vasr

@@ -29,13 +29,13 @@ namespace tc {
 
 constexpr int TN = 128;                 // output time steps per CTA
 constexpr int KC = 32;                  // input channels per chunk
-constexpr int NDW = 8;                  // depthwise warps 0..7
-constexpr int NEPI = 8;                 // epilogue warps 11..18: warp & 3 = 3,0,1,2,3,0,1,2 -> each TMEM lane quarter twice
-constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10, WARP_EPI = 11;
-constexpr int NTHREADS = 19 * 32;
+// Depthwise producer warps: NDW = 8 (thread = channel pair x 8 outputs, 608 threads, <= 104 registers) or NDW = 4
+// (thread = channel pair x 16 outputs: half the shared-memory loads per FMA, 480 threads, <= 136 registers).
+constexpr int NEPI = 8;                 // epilogue warps: any 8 consecutive warps cover each TMEM lane quarter (warp & 3) twice
+__host__ __device__ constexpr int nthreads(int ndw) { return (ndw + 3 + NEPI) * 32; }
 constexpr int MAX_STAGES = 4;           // upper bound of the activation-window / B-operand ring depths
 constexpr int SCHED = 4;                // depth of the tile ring
-constexpr int SCHED_CONSUMERS = 1 /*A*/ + 1 /*MMA*/ + NDW + NEPI;
+__host__ __device__ constexpr int sched_consumers(int ndw) { return 1 /*A*/ + 1 /*MMA*/ + ndw + NEPI; }
 constexpr int PART_BYTES = 128 * KC * 2;   // activation operand: [128 t rows x 64 B] fp16 = 8 KiB per part
 constexpr int W_PART = 256 * KC * 2;       // weight operand:     [256 co rows x 64 B] fp16 = 16 KiB per part
 constexpr int MAX_CO_CTA = 512;
@@ -191,19 +191,53 @@ struct Params {
     int dbg;                  // timing experiments only (VASR_TC_DBG): 1 = skip MMAs, 2 = skip depthwise FMAs, 4 = skip epilogue stores
 };
 
+// Depthwise FIR of one chunk for one thread: channel pair `xs`/`wp` (already offset by the pair), R consecutive outputs
+// starting at window row tw.  Rolling register window, fully unrolled over the taps: window slot of (output r, tap k)
+// holds row tw + r + k*D.  Each tap consumes R FFMA2 and refills D rows + 1 tap weight that are needed P taps later,
+// so shared-memory loads are spread evenly between the FMAs and only R + D*P rows are live.
+template <int K, int D, int R>
+__device__ __forceinline__ void dw_chunk_s1(const float2* __restrict__ xs, const float2* __restrict__ wp, int tw, float2 (&acc)[R])
+{
+    constexpr int XP = KC / 2, wstride = KC / 2;
+    constexpr int P = 4;
+    constexpr int WN = R + D * P;
+    constexpr int LAST_ROW = (K - 1) * D + R - 1;
+    float2 win[WN], wq[P];
+#pragma unroll
+    for (int j = 0; j < WN; ++j) win[j] = (j <= LAST_ROW) ? xs[(size_t)(tw + j) * XP] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < P; ++j) wq[j] = (j < K) ? wp[(size_t)j * wstride] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 wk = wq[k % P];
+        if (k + P < K) wq[k % P] = wp[(size_t)(k + P) * wstride];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[(k * D + r) % WN], acc[r]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int row = k * D + d + WN;                  // replaces the row that just went dead
+            if (row <= LAST_ROW) win[(k * D + d) % WN] = xs[(size_t)(tw + row) * XP];
+        }
+    }
+}
+
 #define PROF_BEGIN() long long _pt = clock64()
 #define PROF_ADD(i) do { long long _n = clock64(); pacc[i] += (unsigned long long)(_n - _pt); _pt = _n; } while (0)
 
 // Persistent CTA (one per SM): tiles are claimed from an atomic counter by the scheduler thread and published
 // to the other roles through a small shared-memory ring; all operand rings and the TMEM accumulator buffers
 // keep running across tiles, so the epilogue of tile i overlaps the depthwise/MMA work of tile i+1.
-template <int K, int S, int D, int NPART>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int K, int S, int D, int NPART, int NDW>
+__global__ void __launch_bounds__(nthreads(NDW), 1)
 subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_r,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
                 const __grid_constant__ CUtensorMap tm_out, const Params p)
 {
+    constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = NDW + 3;
+    constexpr int SCHED_CONSUMERS = sched_consumers(NDW);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve-up: every operand tile must be 1024-byte aligned.  The dynamic window starts right after the driver's
     // 1 KiB reservation, i.e. aligned; the budget has no slack for a round-up, so fail loudly if that ever changes.
@@ -469,10 +503,14 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
         if (p.tma_epi && issuer) bulk_wait_all0();
     } else if (warp < NDW) {
-        // ======== depthwise producers (warps 0..7) ========
-        // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R = 8 outputs:
-        //   cp = lane & 15 -> channels 2cp, 2cp+1 of the chunk;  tg = 2*warp + (lane >> 4) -> t = 8*tg + r
-        constexpr int R = 8;
+        // ======== depthwise producers (warps 0..NDW-1) ========
+        // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R outputs (R = 8 with 8 warps, 16 with 4):
+        //   cp = lane & 15 -> channels 2cp, 2cp+1 of the chunk;  tg = 2*warp + (lane >> 4) -> t = R*tg + r
+        // Every tap costs one window row + one tap weight from shared memory per R FFMA2, so R = 16 halves the
+        // shared-memory load traffic of the stage (the LDS return path, not the FMA pipe, is what the 8-output
+        // version waits on inside the full kernel: profiles/).
+        constexpr int R = TN / (2 * NDW);
+        static_assert(R == 8 || R == 16, "depthwise warps: 4 or 8");
         constexpr int NB = (K % 3 == 0 && K > 17) ? 3 : 1;     // taps are processed in NB register-window blocks
         constexpr int KB = K / NB;
         constexpr int XP = KC / 2;                               // float2 per window row
@@ -500,47 +538,26 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const float2* wp = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes + p.x_w_off) + cp;
                     constexpr int wstride = KC / 2;
                     if (S == 1) {
-                        // Rolling register window, fully unrolled over the taps: window slot of (output r, tap k) holds
-                        // row tw + r + k*D.  Each tap consumes R FFMA2 and refills D rows + 1 tap weight that are needed
-                        // P taps later, so shared-memory loads are spread evenly between the FMAs (no load/compute phases
-                        // shared by all warps) and only R + D*P rows are live.
-                        constexpr int P = 4;
-                        constexpr int WN = R + D * P;
-                        constexpr int LAST_ROW = (K - 1) * D + R - 1;
-                        float2 win[WN], wq[P];
-#pragma unroll
-                        for (int j = 0; j < WN; ++j) win[j] = (j <= LAST_ROW) ? xs[(size_t)(tw + j) * XP] : make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int j = 0; j < P; ++j) wq[j] = (j < K) ? wp[(size_t)j * wstride] : make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const float2 wk = wq[k % P];
-                            if (k + P < K) wq[k % P] = wp[(size_t)(k + P) * wstride];
-#pragma unroll
-                            for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[(k * D + r) % WN], acc[r]);
-#pragma unroll
-                            for (int d = 0; d < D; ++d) {
-                                const int row = k * D + d + WN;                  // replaces the row that just went dead
-                                if (row <= LAST_ROW) win[(k * D + d) % WN] = xs[(size_t)(tw + row) * XP];
-                            }
-                        }
+                        dw_chunk_s1<K, D, R>(xs, wp, tw, acc);
                     } else {
                         // stride 2 (first block only, 2 chunks): tap-blocked window, row of (r, k) = (tw + r) * S + k
 #pragma unroll
                         for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+                        // (8 outputs at a time: the strided window of 16 would not fit the register budget)
+#pragma unroll
+                        for (int h = 0; h < R / 8; ++h) {
 #pragma unroll 1
-                        for (int kb = 0; kb < K; kb += KB) {
-                            constexpr int WIN = (R - 1) * S + KB;
-                            float2 win[WIN];
+                            for (int kb = 0; kb < K; kb += KB) {
+                                constexpr int WIN = 7 * S + KB;
+                                float2 win[WIN];
 #pragma unroll
-                            for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)(tw * S + kb + j) * XP];
+                                for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)((tw + 8 * h) * S + kb + j) * XP];
 #pragma unroll
-                            for (int kk = 0; kk < KB; ++kk) {
-                                const float2 wk = wp[(size_t)(kb + kk) * wstride];
+                                for (int kk = 0; kk < KB; ++kk) {
+                                    const float2 wk = wp[(size_t)(kb + kk) * wstride];
 #pragma unroll
-                                for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[r * S + kk], acc[r]);
+                                    for (int r = 0; r < 8; ++r) acc[8 * h + r] = __ffma2_rn(wk, win[r * S + kk], acc[8 * h + r]);
+                                }
                             }
                         }
                     }
@@ -595,6 +612,401 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     }
 }
 
+// =====================================================================================================================
+// Multi-layer persistent kernel ("segment"): a run of consecutive stride-1 / dilation-1 separable sub-blocks with the
+// same output width and the same number of frames executes as ONE launch.  The work list is layer-major
+// (layer, utterance, time tile); a tile of layer l only needs the tiles of layer l-1 of the SAME utterance (the
+// depthwise halo never leaves the utterance), so instead of a kernel boundary per layer there is one
+// release/acquire counter per (layer, utterance): the epilogue bumps it once its TMA stores have completed, the tile
+// scheduler waits for it before it issues the TMA loads of a dependent tile.  All rings, the TMEM buffers and the
+// roles keep running across layers: no per-layer launch, pipeline fill/drain or partial last wave.
+// =====================================================================================================================
+struct alignas(128) LayerDesc {
+    CUtensorMap tm_x, tm_r, tm_w_hi, tm_w_lo, tm_r_hi, tm_r_lo, tm_out;
+    const float* dw_w;       // [Cin/32][K][32]
+    const float* shift;      // [Cout]
+    const int* len_out;      // [B]
+    float wscale_inv;
+    int K, n_main, n_res, relu, mask_tail, pad;
+    int n_xbox, xbox_rows, x_w_off;
+};
+
+struct SegParams {
+    const LayerDesc* layers;
+    int n_layers;
+    int* tile_counter;       // zeroed before the launch
+    int* done;               // [n_layers][done_stride] completion counters (zeroed): 2 * n_tt per finished (layer, utterance)
+    int done_stride;
+    int T_out, nN;
+    int x_stage_bytes, xstages, bstages, aslots;
+    int b0, n_tt, n_utt;
+    unsigned long long* prof;
+    int dbg;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+#define SEG_K_SWITCH(Kv, STMT)                                   \
+    switch (Kv) {                                                \
+        case 11: { constexpr int KK = 11; STMT; } break;         \
+        case 33: { constexpr int KK = 33; STMT; } break;         \
+        case 39: { constexpr int KK = 39; STMT; } break;         \
+        case 51: { constexpr int KK = 51; STMT; } break;         \
+        case 63: { constexpr int KK = 63; STMT; } break;         \
+        default: { constexpr int KK = 75; STMT; } break;         \
+    }
+static bool seg_kernel_size(int K) { return K == 11 || K == 33 || K == 39 || K == 51 || K == 63 || K == 75; }
+
+template <int NPART, int NDW>
+__global__ void __launch_bounds__(nthreads(NDW), 1)
+segment_kernel(const SegParams p)
+{
+    constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = NDW + 3;
+    constexpr int SCHED_CONSUMERS = sched_consumers(NDW);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    unsigned char* smem = smem_raw;
+    constexpr int A_SLOT = W_PART * NPART, B_STAGE = PART_BYTES * NPART;
+    unsigned char* a_ring = smem;
+    unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
+    unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
+    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;      // [2][128 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 2 * EPI_STAGE_BYTES);
+    const int XSTAGES = p.xstages, BSTAGES = p.bstages;
+    uint64_t* full_x = bars;
+    uint64_t* empty_x = full_x + MAX_STAGES;
+    uint64_t* full_b = empty_x + MAX_STAGES;
+    uint64_t* empty_b = full_b + MAX_STAGES;
+    uint64_t* full_a = empty_b + MAX_STAGES;
+    uint64_t* empty_a = full_a + 16;
+    uint64_t* acc_full = empty_a + 16;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* sched_full = acc_empty + 2;
+    uint64_t* sched_empty = sched_full + SCHED;
+    int* tile_ring = reinterpret_cast<int*>(sched_empty + SCHED);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + SCHED);
+    float* ep_shift = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long pacc[4] = {0ull, 0ull, 0ull, 0ull};
+    const int tpl = p.n_tt * p.n_utt;                      // tiles per layer
+    const int n_items = tpl * p.n_layers;
+    const int acc_cols = p.nN * 256;
+    const int nbuf = (acc_cols <= 256) ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, NDW); }
+        for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, NDW); mbar_init(empty_b + i, 1); }
+        for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, NEPI); }
+        for (int i = 0; i < SCHED; ++i) { mbar_init(sched_full + i, 1); mbar_init(sched_empty + i, SCHED_CONSUMERS); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // item -> (layer, utterance, time tile)
+    auto decode = [&](int item, int& l, int& b, int& t0) {
+        l = item / tpl;
+        const int r = item - l * tpl;
+        b = p.b0 + r / p.n_tt;
+        t0 = (r % p.n_tt) * TN;
+    };
+    auto next_tile = [&](int ti) -> int {
+        const int slot = ti % SCHED;
+        mbar_wait(sched_full + slot, (ti / SCHED) & 1);
+        const int tile = tile_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sched_empty + slot);
+        return tile;
+    };
+
+    if (warp == WARP_X) {
+        // ======== scheduler (+ cross-layer dependency wait) + TMA producer of the activation window ========
+        if (lane == 0) {
+            int s = 0; uint32_t xph = 0;
+            for (int ti = 0;; ++ti) {
+                const int slot = ti % SCHED;
+                mbar_wait(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
+                int tile = atomicAdd(p.tile_counter, 1);
+                if (tile >= n_items) tile = -1;
+                tile_ring[slot] = tile;
+                mbar_arrive(sched_full + slot);
+                if (tile < 0) break;
+                int l, b, t0;
+                decode(tile, l, b, t0);
+                const LayerDesc* L = p.layers + l;
+                if (l > 0) {
+                    // every tile of layer l-1 of this utterance has been stored (both epilogue halves of each time tile)
+                    const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
+                    const int need = 2 * p.n_tt;
+                    PROF_BEGIN();
+                    while (ld_acquire_gpu(flag) < need) __nanosleep(40);
+                    PROF_ADD(1);
+                    fence_proxy_async_all();        // the TMA (async proxy) reads below are ordered after the acquire
+                }
+                const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res;
+                const int n_xbox = L->n_xbox, xbox_rows = L->xbox_rows, x_w_off = L->x_w_off, pad = L->pad;
+                const float* dw_w = L->dw_w;
+                for (int c = 0; c < nch; ++c) {
+                    PROF_BEGIN();
+                    mbar_wait(empty_x + s, xph ^ 1);
+                    PROF_ADD(0);
+                    unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
+                    if (c < n_main) {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + K * KC * 4));
+                        for (int j = 0; j < n_xbox; ++j)
+                            tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + s);
+                        bulk_load(dst + x_w_off, dw_w + (size_t)c * K * KC, (uint32_t)(K * KC * 4), full_x + s);
+                    } else {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
+                        tma_load_3d(dst, &L->tm_r, (c - n_main) * KC, t0, b, full_x + s);
+                    }
+                    if (++s == XSTAGES) { s = 0; xph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == WARP_A) {
+        // ======== TMA producer: weight slots ========
+        int slot = 0; uint32_t ph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            if (lane == 0) {
+                int l, b, t0;
+                decode(tile, l, b, t0);
+                const LayerDesc* L = p.layers + l;
+                const int n_main = L->n_main, nch = L->n_main + L->n_res;
+                for (int c = 0; c < nch; ++c) {
+                    const bool res = c >= n_main;
+                    const int ci0 = (res ? c - n_main : c) * KC;
+                    for (int m = 0; m < p.nN; ++m) {
+                        PROF_BEGIN();
+                        mbar_wait(empty_a + slot, ph ^ 1);
+                        PROF_ADD(0);
+                        mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
+                        unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
+                        tma_load_2d(dst, res ? &L->tm_r_hi : &L->tm_w_hi, ci0, m * 256, full_a + slot);
+                        if (NPART == 2) tma_load_2d(dst + W_PART, res ? &L->tm_r_lo : &L->tm_w_lo, ci0, m * 256, full_a + slot);
+                        if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == WARP_MMA) {
+        // ======== tcgen05.mma issuer (one thread) ========
+        int slot = 0; uint32_t ph = 0;
+        int sb = 0; uint32_t bph = 0;
+        int ab = 0; uint32_t accph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            if (lane == 0) {
+                int l, b, t0;
+                decode(tile, l, b, t0);
+                const int nch = p.layers[l].n_main + p.layers[l].n_res;
+                PROF_BEGIN();
+                mbar_wait(acc_empty + ab, accph ^ 1);
+                PROF_ADD(2);
+                tcgen05_fence_after();
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(full_b + sb, bph);
+                    PROF_ADD(0);
+                    tcgen05_fence_after();
+                    const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
+                    for (int m = 0; m < p.nN; ++m) {
+                        mbar_wait(full_a + slot, ph);
+                        PROF_ADD(1);
+                        tcgen05_fence_after();
+                        const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
+                        const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 256);
+#pragma unroll
+                        for (int ks = 0; ks < KC / 16; ++ks) {
+                            const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
+                            const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                            umma_f16(d, x_hi, w_hi, IDESC_F16_M128_N256, (c > 0 || ks > 0) ? 1u : 0u);
+                            if (NPART == 2) {
+                                const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
+                                const uint64_t w_lo = make_desc_sw64(w_addr + W_PART + ks * 32);
+                                umma_f16(d, x_lo, w_hi, IDESC_F16_M128_N256, 1u);
+                                umma_f16(d, x_hi, w_lo, IDESC_F16_M128_N256, 1u);
+                            }
+                        }
+                        tcgen05_commit(empty_a + slot);
+                        PROF_ADD(3);
+                        if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                    }
+                    tcgen05_commit(empty_b + sb);
+                    if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                }
+                tcgen05_commit(acc_full + ab);
+                if (++ab == nbuf) { ab = 0; accph ^= 1; }
+            }
+            __syncwarp();
+        }
+    } else if (warp >= WARP_EPI) {
+        // ======== epilogue (8 warps): TMEM -> +shift, ReLU, mask -> smem staging -> TMA store -> completion counter ========
+        const int q = warp & 3;
+        const int half = (warp - WARP_EPI) >> 2;
+        const int row = q * 32 + lane;
+        const bool issuer = (q == 0 && lane == 0);
+        unsigned char* stage = epi_stage + half * EPI_STAGE_BYTES;
+        const int nslice = p.nN * 4;
+        int cur_l = -1;
+        float wsc = 1.f; int relu = 0, mask_tail = 1; const int* len_out = nullptr;
+        int ab = 0; uint32_t accph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int l, b, t0;
+            decode(tile, l, b, t0);
+            const LayerDesc* L = p.layers + l;
+            if (l != cur_l) {                                  // per-channel BN shift + scalars of the new layer
+                named_bar_sync(3, NEPI * 32);
+                const float* shift = L->shift;
+                for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI * 32) ep_shift[i] = __ldg(shift + i);
+                wsc = L->wscale_inv; relu = L->relu; mask_tail = L->mask_tail; len_out = L->len_out;
+                named_bar_sync(3, NEPI * 32);
+                cur_l = l;
+            }
+            const int t = t0 + row;
+            const bool live = !(mask_tail && t >= len_out[b]);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
+            auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
+            PROF_BEGIN();
+            mbar_wait(acc_full + ab, accph);
+            PROF_ADD(0);
+            tcgen05_fence_after();
+            const int ab_cur = ab;
+            if (++ab == nbuf) { ab = 0; accph ^= 1; }
+            uint32_t ra[32];
+#pragma unroll 1
+            for (int sidx = 0; sidx < nslice; ++sidx) {
+                const int col0 = slice_col(sidx);
+                tmem_ld_32x32b_x32(tbase + (uint32_t)col0, ra);
+                tmem_ld_wait();
+                if (sidx + 1 == nslice) {                      // every TMEM read of this tile has completed
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + ab_cur);
+                }
+                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                if (issuer) bulk_wait_read0();                 // previous slice has left the staging buffer
+                named_bar_sync(1 + half, 128);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 sh = sh4[i];
+                    float4 v;
+                    v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, sh.x);
+                    v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, sh.y);
+                    v.z = fmaf(__uint_as_float(ra[4 * i + 2]), wsc, sh.z);
+                    v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, sh.w);
+                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
+                }
+                fence_proxy_async();
+                named_bar_sync(1 + half, 128);
+                if (issuer) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
+            }
+            if (issuer) {
+                // this half's part of the tile is in global memory: publish it to the tiles of the next layer
+                bulk_wait_all0();
+                fence_proxy_async_all();
+                __threadfence();
+                atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
+            }
+            PROF_ADD(1);
+        }
+    } else if (warp < NDW) {
+        // ======== depthwise producers ========
+        constexpr int R = TN / (2 * NDW);
+        constexpr int XP = KC / 2;
+        const int cp = lane & 15;
+        const int tw = (warp * 2 + (lane >> 4)) * R;
+        int sx = 0, sb = 0; uint32_t xph = 0, bph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int l, b, t0;
+            decode(tile, l, b, t0);
+            const LayerDesc* L = p.layers + l;
+            const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res, x_w_off = L->x_w_off;
+            const int len_mid = L->len_out[b];
+            const bool tail_tile = t0 + TN > len_mid;      // only tiles that straddle the utterance's end need the row mask
+            for (int c = 0; c < nch; ++c) {
+                PROF_BEGIN();
+                mbar_wait(full_x + sx, xph);
+                PROF_ADD(0);
+                const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
+                float2 acc[R];
+                if (c < n_main) {
+                    const float2* wp = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes + x_w_off) + cp;
+                    SEG_K_SWITCH(K, (dw_chunk_s1<KK, 1, R>(xs, wp, tw, acc)));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
+                }
+                if (tail_tile) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
+                }
+                PROF_ADD(1);
+                mbar_wait(empty_b + sb, bph ^ 1);
+                PROF_ADD(2);
+                unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = tw + r;
+                    const uint32_t off = sw64_offset(row, cp >> 2) + (cp & 3) * 4;
+                    const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
+                    *reinterpret_cast<__half2*>(bh + off) = h;
+                    if (NPART == 2) {
+                        const float2 hf = __half22float2(h);
+                        *reinterpret_cast<__half2*>(bh + PART_BYTES + off) = __floats2half2_rn(acc[r].x - hf.x, acc[r].y - hf.y);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(full_b + sb); mbar_arrive(empty_x + sx); }
+                if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
+                if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                PROF_ADD(3);
+            }
+        }
+    }
+    if (p.prof && lane == 0) {
+        // slots as in subblock_kernel; slot 5 (xprod) additionally: cycles spent waiting for a cross-layer dependency
+        int base = -1;
+        if (warp == 0) base = 0; else if (warp == WARP_X) base = 4; else if (warp == WARP_A) base = 12;
+        else if (warp == WARP_MMA) base = 6; else if (warp == WARP_EPI) base = 10;
+        if (base >= 0)
+            for (int i = 0; i < 4; ++i)
+                if (pacc[i]) atomicAdd(p.prof + base + i, pacc[i]);
+        if (warp == 1) atomicAdd(p.prof + 15, 1ull);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int encode_tm(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
                      const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw)
@@ -632,8 +1044,9 @@ static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin)
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-struct KernelEntry { int K, S, D; const void* fn[2]; };
-#define TC_ENTRY(k, s, d) {k, s, d, {(const void*)subblock_kernel<k, s, d, 2>, (const void*)subblock_kernel<k, s, d, 1>}}
+struct KernelEntry { int K, S, D; const void* fn[2][2]; };   // [f16x3 ? 0 : 1][8 dw warps ? 0 : 1 (4 dw warps)]
+#define TC_ENTRY(k, s, d) {k, s, d, {{(const void*)subblock_kernel<k, s, d, 2, 8>, (const void*)subblock_kernel<k, s, d, 2, 4>}, \
+                                     {(const void*)subblock_kernel<k, s, d, 1, 8>, (const void*)subblock_kernel<k, s, d, 1, 4>}}}
 static const KernelEntry g_kernels[] = {
     TC_ENTRY(1, 1, 1), TC_ENTRY(33, 2, 1), TC_ENTRY(33, 1, 1), TC_ENTRY(39, 1, 1), TC_ENTRY(51, 1, 1),
     TC_ENTRY(63, 1, 1), TC_ENTRY(75, 1, 1), TC_ENTRY(87, 1, 2), TC_ENTRY(11, 1, 1), TC_ENTRY(11, 2, 1), TC_ENTRY(15, 1, 2),
@@ -678,6 +1091,8 @@ static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int*
 
 }  // namespace tc
 
+static std::atomic<unsigned long long> g_layer_uid{1};
+
 int tc_init()
 {
     using namespace tc;
@@ -693,7 +1108,10 @@ int tc_init()
     VASR_CUDA_OK(cudaDeviceGetAttribute(&tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     for (const KernelEntry& e : g_kernels)
         for (int i = 0; i < 2; ++i)
-            VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+            for (int j = 0; j < 2; ++j)
+                VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return VASR_OK;
 }
 
@@ -715,6 +1133,7 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
 {
     using namespace tc;
     const int Co = sb.cout, Ci = sb.cin, Cr = sb.has_res ? sb.res_cin : 0;
+    sb.uid = g_layer_uid.fetch_add(1);
     std::vector<__half> mh((size_t)Co * Ci), ml((size_t)Co * Ci), rh((size_t)Co * Cr), rl((size_t)Co * Cr);
     // one power-of-two pre-scale per layer: the largest |w| lands in [2^13, 2^14), so hi and lo = w - hi stay in
     // fp16's normal range for every weight within 2^17 of the maximum (smaller ones lose lo bits that are below
@@ -837,7 +1256,10 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
     p.prof = prof_on ? d_prof : nullptr;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
-    VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
+    // depthwise warps per CTA: 4 (16 outputs per thread) by default, VASR_TC_NDW=8 selects the 8-warp variant
+    static int ndw = -1;
+    if (ndw < 0) { const char* e = getenv("VASR_TC_NDW"); ndw = (e && atoi(e) == 8) ? 8 : 4; }
+    VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1][ndw == 8 ? 0 : 1], grid, dim3(nthreads(ndw)), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (prof_on) {
         unsigned long long h[16];
@@ -848,6 +1270,128 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
                 K, sb.cin, sb.cout, (int)sb.has_res, n_tiles, (int)grid.x, p.xstages, p.bstages, p.aslots,
                 h[0] / n / 1e3, h[1] / n / 1e3, h[2] / n / 1e3, h[3] / n / 1e3, h[4] / n / 1e3, h[5] / n / 1e3,
                 h[6] / n / 1e3, h[7] / n / 1e3, h[8] / n / 1e3, h[9] / n / 1e3, h[10] / n / 1e3, h[11] / n / 1e3);
+    }
+    return VASR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ segment launch
+
+struct SegCacheEntry {
+    unsigned long long uid; int n; const void* x_first; const void* y_last; int B, T;
+    tc::LayerDesc* d_desc;
+    int x_stage_bytes;
+};
+static std::vector<SegCacheEntry> g_seg_cache;   // device descriptor tables, keyed by (model layer, buffers, shape)
+
+bool segment_tc_layer_ok(const SubBlock& sb)
+{
+    using namespace tc;
+    if (!sb.separable || sb.stride != 1 || sb.dilation != 1 || sb.final_layer) return false;
+    if (!seg_kernel_size(sb.kernel)) return false;
+    if (!subblock_tc_supported(sb)) return false;
+    if (sb.cout > MAX_CO_CTA) return false;
+    return true;
+}
+
+static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes, int* xstages, int* bstages, int* aslots)
+{
+    using namespace tc;
+    int mx = 0;
+    for (int i = 0; i < n; ++i) {
+        int nb, br, wo, sbytes;
+        x_geometry(L[i].sb->kernel, 1, 1, &nb, &br, &wo, &sbytes);
+        if (sbytes > mx) mx = sbytes;
+    }
+    *x_stage_bytes = mx;
+    pick_rings(npart, mx, L[0].sb->cout / 256, 2 * EPI_STAGE_BYTES, xstages, bstages, aslots);
+}
+
+bool segment_tc_ok(const SegLayer* L, int n, int split3)
+{
+    using namespace tc;
+    if (n < 2) return false;
+    for (int i = 0; i < n; ++i) {
+        if (!segment_tc_layer_ok(*L[i].sb)) return false;
+        if (L[i].sb->cout != L[0].sb->cout) return false;
+    }
+    int xsb, xs, bs, as;
+    seg_geometry(L, n, split3 ? 2 : 1, &xsb, &xs, &bs, &as);
+    return as >= L[0].sb->cout / 256;
+}
+
+int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0, int nb,
+                      int* tile_counter, int* done, int done_stride, int grid_limit, cudaStream_t st)
+{
+    using namespace tc;
+    if (!segment_tc_ok(L, n, split3)) return set_error(VASR_EINVAL, "tcgen05 path: layers do not form a segment");
+    const int npart = split3 ? 2 : 1;
+    SegParams p{};
+    seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots);
+    p.nN = L[0].sb->cout / 256;
+    // descriptor table (tensor maps + per-layer scalars) in device memory, cached per (layer, buffers, shape)
+    LayerDesc* d_desc = nullptr;
+    for (const SegCacheEntry& e : g_seg_cache)
+        if (e.uid == L[0].sb->uid && e.n == n && e.x_first == L[0].x && e.y_last == L[n - 1].y && e.B == B && e.T == T) { d_desc = e.d_desc; break; }
+    if (!d_desc) {
+        std::vector<LayerDesc> h((size_t)n);
+        int rc;
+        for (int i = 0; i < n; ++i) {
+            const SubBlock& sb = *L[i].sb;
+            LayerDesc& d = h[i];
+            memset(&d, 0, sizeof(d));
+            int stage_bytes;
+            x_geometry(sb.kernel, 1, 1, &d.n_xbox, &d.xbox_rows, &d.x_w_off, &stage_bytes);
+            if ((rc = encode_act(&d.tm_x, L[i].x, B, T, sb.cin, L[i].xs, d.xbox_rows))) return rc;
+            if (sb.has_res) { if ((rc = encode_act(&d.tm_r, L[i].res, B, T, sb.res_cin, L[i].rs, TN))) return rc; }
+            else d.tm_r = d.tm_x;
+            memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
+            memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
+            if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys))) return rc;
+            d.dw_w = sb.dw_tc; d.shift = sb.shift; d.len_out = L[i].len_out; d.wscale_inv = sb.wscale_inv_scalar;
+            d.K = sb.kernel; d.n_main = sb.cin / KC; d.n_res = sb.has_res ? sb.res_cin / KC : 0;
+            d.relu = sb.relu ? 1 : 0; d.mask_tail = 1; d.pad = sb.pad;
+        }
+        if (g_seg_cache.size() >= 64) {                      // bounded: drop everything once nothing can still be reading it
+            VASR_CUDA_OK(cudaDeviceSynchronize());
+            for (SegCacheEntry& e : g_seg_cache) cudaFree(e.d_desc);
+            g_seg_cache.clear();
+        }
+        VASR_CUDA_OK(cudaMalloc((void**)&d_desc, sizeof(LayerDesc) * (size_t)n));
+        VASR_CUDA_OK(cudaMemcpy(d_desc, h.data(), sizeof(LayerDesc) * (size_t)n, cudaMemcpyHostToDevice));
+        g_seg_cache.push_back(SegCacheEntry{L[0].sb->uid, n, L[0].x, L[n - 1].y, B, T, d_desc, p.x_stage_bytes});
+    }
+    p.layers = d_desc; p.n_layers = n;
+    p.tile_counter = tile_counter; p.done = done; p.done_stride = done_stride;
+    p.T_out = T; p.b0 = b0; p.n_tt = ceil_div(T, TN); p.n_utt = nb;
+    const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
+                        (size_t)p.xstages * p.x_stage_bytes + 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
+    const long long n_items = (long long)p.n_tt * p.n_utt * n;
+    int max_ctas = g_num_sms;
+    if (grid_limit > 0 && grid_limit < max_ctas) max_ctas = grid_limit;
+    dim3 grid((unsigned)(n_items < max_ctas ? n_items : max_ctas), 1, 1);
+    static int prof_on = -1;
+    static unsigned long long* d_prof = nullptr;
+    if (prof_on < 0) {
+        const char* e = getenv("VASR_TC_PROF");
+        prof_on = (e && atoi(e) > 0) ? 1 : 0;
+        if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    }
+    p.prof = prof_on ? d_prof : nullptr;
+    p.dbg = 0;
+    if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
+    void* args[] = {(void*)&p};
+    const void* fn = split3 ? (const void*)segment_kernel<2, 4> : (const void*)segment_kernel<1, 4>;
+    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(nthreads(4)), args, smem, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (prof_on) {
+        unsigned long long h[16];
+        VASR_CUDA_OK(cudaStreamSynchronize(st));
+        VASR_CUDA_OK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        const double c = (double)(h[15] ? h[15] : 1);
+        fprintf(stderr, "TCSEG layers=%d k=%d..%d cout=%d items=%lld ctas=%d xs=%d bs=%d as=%d | dw: wait_x %.0f comp %.0f wait_b %.0f store %.0f | xprod wait %.0f dep %.0f | aprod wait %.0f | mma: wait_b %.0f wait_a %.0f wait_acc %.0f issue %.0f | epi: wait %.0f drain %.0f (kcycles per CTA)\n",
+                n, L[0].sb->kernel, L[n - 1].sb->kernel, L[0].sb->cout, n_items, (int)grid.x, p.xstages, p.bstages, p.aslots,
+                h[0] / c / 1e3, h[1] / c / 1e3, h[2] / c / 1e3, h[3] / c / 1e3, h[4] / c / 1e3, h[5] / c / 1e3, h[12] / c / 1e3,
+                h[6] / c / 1e3, h[7] / c / 1e3, h[8] / c / 1e3, h[9] / c / 1e3, h[10] / c / 1e3, h[11] / c / 1e3);
     }
     return VASR_OK;
 }

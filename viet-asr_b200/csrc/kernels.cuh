@@ -28,6 +28,18 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
                        int* tile_counter, int grid_limit, cudaStream_t st);
 bool subblock_tc_supported(const SubBlock& sb);
+// multi-layer persistent launch over a run of stride-1 separable sub-blocks with the same cout and frame count
+struct SegLayer {
+    SubBlock* sb;
+    const float* x; long long xs;      // input [B, T, cin] + batch stride (elements)
+    const float* res; long long rs;    // residual-branch input (block input) or null
+    float* y; long long ys;            // output [B, T, cout]
+    const int* len_out;                // [B]
+};
+bool segment_tc_layer_ok(const SubBlock& sb);
+bool segment_tc_ok(const SegLayer* L, int n, int split3);
+int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0, int nb,
+                      int* tile_counter, int* done, int done_stride, int grid_limit, cudaStream_t st);
 int tc_init();
 // w_main [cout][cin], w_res [cout][res_cin] (or null): BN-scale-folded fp32 weights on the host
 int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, const float* dw_kc /*[K][cin] or null*/,
