@@ -49,12 +49,13 @@ def load_peaks():
 
 
 def load_traffic(mode):
-    """dram__bytes_read.sum + dram__bytes_write.sum per subblock_kernel launch from the committed ncu capture
-    (profiles/r1_traffic.json, f16x3, same workload); None for other modes."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the encoder kernels of ONE step from the committed ncu
+    capture (profiles/r1_traffic.json, f16x3, same workload); None for other modes."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if mode != "f16x3" or not os.path.exists(p):
         return None
-    return json.load(open(p))["traffic_bytes_per_launch"]
+    d = json.load(open(p))
+    return d.get("traffic_bytes_per_step", d.get("traffic_bytes_per_launch", 0) * d.get("launches", 0))
 
 
 def algorithmic_counts(jasper, feat_in, T_f, num_classes):
@@ -320,6 +321,12 @@ def main():
     for _ in range(W):
         step_device()
     barrier()
+    _feat, _seq = eng.preprocessor.forward_channels_last(wave_d, len_d)
+    _l0 = V._lib.launch_count()
+    eng.encoder.forward_channels_last(_feat, _seq)
+    enc_launches = int(V._lib.launch_count() - _l0)      # kernels of one encoder pass (incl. the length kernel)
+    del _feat, _seq
+    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = V._lib.launch_count()
     step_ev = [(ev(), ev(), ev(), ev()) for _ in range(K)]
@@ -427,20 +434,39 @@ def main():
     peaks = load_peaks()
     enc_bytes = B * counts["bytes_act"] + counts["weight_bytes"]
     enc_flops_tc = B * (counts["flops_pw"] + counts["flops_res"])
+    enc_flops_dw = B * counts["flops_dw"]
     n_sub = counts["n_sub"]
     ach_gbs = enc_bytes / (enc_ms_avg * 1e-3) / 1e9
     ach_tf = enc_flops_tc / (enc_ms_avg * 1e-3) / 1e12
+    ach_dw_tf = enc_flops_dw / (enc_ms_avg * 1e-3) / 1e12
+    # FP32 pipe peak from the committed micro-benchmark (tools/ubench/fma_rate, profiles/r1_ubench_fma_rate.log):
+    # packed FFMA2 sustains 125 FMA lanes per clock per SM
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak_tf = 125.0 * 2 * 148 * sm_mhz * 1e6 / 1e12
+    traffic_step = load_traffic(args.mode)
     roofline = {
-        "kernel": "subblock_kernel (fused depthwise + tcgen05 1x1 conv + BN + ReLU)" if args.mode != "fp32"
+        "kernel": "segment_kernel / subblock_kernel (fused depthwise + tcgen05 1x1 conv + BN + ReLU; one launch per "
+                  "run of same-width sub-blocks and sub-batch)" if args.mode != "fp32"
                   else "dw_conv_kernel + pw_gemm_kernel (CUDA-core path)",
         "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": ach_gbs / peaks["hbm_gbs"], "traffic": load_traffic(args.mode), "peak_source": peaks["source"] + " (burst copy)",
-        "launches_per_step": n_sub, "avg_launch_ms": enc_ms_avg / n_sub,
-        "algorithmic_bytes_per_launch": enc_bytes / n_sub,
+        "frac": ach_gbs / peaks["hbm_gbs"],
+        "traffic": (traffic_step / enc_launches) if (traffic_step and enc_launches) else None,
+        "peak_source": peaks["source"] + " (burst copy)",
+        "what": "all encoder launches of a step taken together: algorithmic bytes of the 78 sub-blocks / encoder-stage time "
+                "(CUDA events inside the timed region)",
+        "launches_per_step": enc_launches, "sub_blocks_per_step": n_sub,
+        "avg_launch_ms": enc_ms_avg / max(1, enc_launches),
+        "algorithmic_bytes_per_launch": enc_bytes / max(1, enc_launches),
+        "algorithmic_bytes_per_sub_block": enc_bytes / n_sub,
         "tensor": {"achieved": ach_tf, "unit": "TFLOP/s (algorithmic 1x1-conv flops)",
                    "peak": peaks["bf16_tflops"], "frac": ach_tf / peaks["bf16_tflops"],
                    "products_per_mac": 3 if args.mode == "f16x3" else 1,
+                   "frac_of_issued_mma": (3 if args.mode == "f16x3" else 1) * ach_tf / peaks["bf16_tflops"],
                    "note": "peak = measured sustained bf16 cuBLAS; f16x3 issues 3 fp16 MMAs per algorithmic MAC"},
+        "fp32_pipe": {"achieved": ach_dw_tf, "unit": "TFLOP/s (depthwise FMAs on the CUDA cores)", "peak": fp32_peak_tf,
+                      "frac": ach_dw_tf / fp32_peak_tf,
+                      "note": "the co-limiter SURVEY 8(d) names: the depthwise stage runs as packed FFMA2; peak = measured "
+                              "125 FMA lanes/clk/SM x 148 SMs x SM clock under load"},
     }
     cpu = None
     if not args.no_cpu_baseline:

@@ -199,6 +199,24 @@ int  vasr_ctc_beam_search_lm(const float* log_probs, int B, int T, int V, int bl
                              void* workspace, size_t workspace_bytes,
                              int32_t* out_ids, int32_t* out_len, float* out_score, void* stream);
 
+/* ---- audio ingest: PCM decode + sample-rate conversion ------------------- */
+/* What the reference's callers do on the CPU before VietASR.transcribe: int16 PCM -> float32 (x / 2^15, the
+ * soundfile/librosa convention, nemo/collections/asr/parts/segment.py:61-74) and librosa.load(path, sr=16000)
+ * (infer.py:200, app.py:66,82) = resampy "kaiser_best" windowed-sinc interpolation, output length
+ * ceil(n * sr_out / sr_in).  librosa/resampy are un-vendored: restated from the published algorithm, parity with
+ * the packages UNPINNED (oracle/resample_oracle.py).
+ * interp_win_host: right half of the low-pass (num_zeros * num_table + 1 samples, num_table per zero crossing). */
+typedef struct vasr_resampler vasr_resampler;
+int  vasr_resampler_create(const float* interp_win_host, int n_win, int num_table, vasr_resampler** out);
+void vasr_resampler_destroy(vasr_resampler* rs);
+int64_t vasr_resample_out_len(int64_t n_in, int sr_in, int sr_out);
+/* pcm [B, L] i16, length [B] i64 -> wave [B, L] f32 (zero beyond length)                                         */
+int  vasr_pcm16_to_float(const int16_t* pcm, const int64_t* length, int B, int64_t L, float* wave, void* stream);
+/* x [B, L_in] (f32, or i16 PCM when pcm16 != 0), len_in [B] i64 -> y [B, L_out] f32 (zero beyond len_out),
+ * len_out [B] i64; L_out >= vasr_resample_out_len(L_in, sr_in, sr_out).  All device pointers.                    */
+int  vasr_resample(const vasr_resampler* rs, const void* x, int pcm16, const int64_t* len_in, int B, int64_t L_in,
+                   int sr_in, int sr_out, float* y, int64_t* len_out, int64_t L_out, void* stream);
+
 /* ---- whole path, HOST buffers (the reference-facing plugin call) ------- */
 /* wave_host [B, L] f32 and length_host [B] i64 in (pinned or pageable) host memory;
  * out_ids_host [B, T_e] i32 (-1 padded) and out_len_host [B] i32 in host memory.

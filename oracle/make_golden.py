@@ -136,10 +136,77 @@ def copy_language_models():
         print("copied", name, os.path.getsize(os.path.join(dst, name)), "bytes")
 
 
+def write_wer_cases():
+    """Accuracy metric: run the reference's own `word_error_rate`
+    (nemo/collections/asr/metrics.py:30-63, imported unmodified by file path - it only needs torch) on seeded
+    hypothesis / reference pairs built from the shipped corpus and write inputs + outputs to
+    tests/golden/wer_cases.json."""
+    import json
+    import random
+    spec = importlib.util.spec_from_file_location("ref_metrics", os.path.join(REF, "nemo/collections/asr/metrics.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = random.Random(20260925)
+    corpus = os.path.join(REF, "models/language_model/alltext.txt")
+    lines = []
+    if os.path.exists(corpus):
+        with open(corpus, encoding="utf-8") as f:
+            for i, ln in enumerate(f):
+                if i >= 4000:
+                    break
+                ln = ln.strip()
+                if 3 <= len(ln.split()) <= 24:
+                    lines.append(ln)
+    if not lines:
+        lines = ["xin chào các bạn", "hôm nay trời đẹp quá", "một hai ba bốn năm sáu bảy"]
+    rng.shuffle(lines)
+
+    def corrupt(s):
+        w = s.split()
+        out = []
+        for x in w:
+            r = rng.random()
+            if r < 0.12:
+                continue                                   # deletion
+            if r < 0.24:
+                out.append(rng.choice(lines).split()[0])   # substitution
+                continue
+            if r < 0.32:
+                out.append(x[:-1] if len(x) > 1 else x + "a")   # character edit
+                continue
+            out.append(x)
+            if r > 0.93:
+                out.append(rng.choice(lines).split()[-1])  # insertion
+        return " ".join(out)
+
+    cases = []
+    for n in (1, 2, 5, 16):
+        refs = [lines[rng.randrange(len(lines))] for _ in range(n)]
+        hyps = [corrupt(r) for r in refs]
+        cases.append({"hyp": hyps, "ref": refs})
+    cases.append({"hyp": ["", "a b"], "ref": ["a b c", ""]})
+    cases.append({"hyp": ["a  b   c"], "ref": ["a b c"]})
+    cases.append({"hyp": [""], "ref": [""]})                  # -> inf
+    cases.append({"hyp": ["same words here"], "ref": ["same words here"]})
+    for c in cases:
+        for cer in (False, True):
+            v = mod.word_error_rate(c["hyp"], c["ref"], use_cer=cer)
+            c["cer" if cer else "wer"] = "inf" if v == float("inf") else v
+    path = os.path.join(ROOT, "tests/golden/wer_cases.json")
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump({"source": "nemo/collections/asr/metrics.py word_error_rate run by oracle/make_golden.py", "cases": cases},
+                  f, ensure_ascii=False, indent=1)
+    print("wrote", path, len(cases), "cases")
+
+
 def main():
+    if "--wer-only" in sys.argv:
+        write_wer_cases()
+        return
     copy_language_models()
     if "--lm-only" in sys.argv:
         return
+    write_wer_cases()
     parts = load_ref_parts()
     os.makedirs(os.path.join(ROOT, "tests/golden"), exist_ok=True)
     os.makedirs(os.path.join(ROOT, "weights"), exist_ok=True)

@@ -73,6 +73,11 @@ PROTOTYPES = {
     "vasr_ctc_beam_lm_workspace_bytes": (_sz, [_i, _i, _i]),
     "vasr_ctc_beam_search_lm": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, C.c_double, C.c_double,
                                      C.c_double, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "vasr_resampler_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "vasr_resampler_destroy": (None, [_vp]),
+    "vasr_resample_out_len": (_i64, [_i64, _i, _i]),
+    "vasr_pcm16_to_float": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "vasr_resample": (_i, [_vp, _vp, _i, _vp, _i, _i64, _i, _i, _vp, _vp, _i64, _vp]),
     "vasr_transcribe_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
 }
 

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import _lib, asr, configs
+from . import _lib, asr, audio, configs
 from .nm import DeviceType, NeuralModuleFactory
 
 
@@ -129,6 +129,58 @@ class VietASR:
             ids, n = self.transcribe_host_ids(w.pin_memory(), lens.pin_memory())
             return asr.ids_to_text(ids, n, self.labels)
         return self.beam_batch_device(w.cuda(non_blocking=True), lens.cuda(non_blocking=True))
+
+    # ---- batched, length-aware data path in front of the kernels
+    @torch.no_grad()
+    def transcribe_signals(self, signals: Sequence[np.ndarray], sample_rates, decoder: Optional[str] = None,
+                           batch_size: int = 256, max_padded_seconds: float = 2560.0,
+                           max_duration: Optional[float] = None) -> List[Optional[str]]:
+        """Mono signals (int16 PCM or float32) at their native sample rates -> transcripts, in input order.
+
+        What `infer.py:196-206` / `app.py:58-91` do one file at a time - `librosa.load(path, sr=16000)` then
+        `transcribe` - as a batched device pipeline: utterances are bucketed by length (per sample rate), zero-padded
+        (`seq_collate_fn` layout), copied once, converted / resampled to the model rate on the GPU and decoded.
+        `max_duration` mirrors the CLI's skip of clips longer than 10 s (infer.py:201-203): those come back as None."""
+        kind = decoder or self.decoder_kind
+        if isinstance(sample_rates, int):
+            sample_rates = [sample_rates] * len(signals)
+        if len(sample_rates) != len(signals):
+            raise ValueError("transcribe_signals: one sample rate per signal")
+        out: List[Optional[str]] = [None] * len(signals)
+        if not hasattr(self, "_resampler"):
+            self._resampler = audio.Resampler()
+        by_sr: Dict[int, List[int]] = {}
+        for i, (s, sr) in enumerate(zip(signals, sample_rates)):
+            n = int(np.asarray(s).shape[0])
+            if n == 0 or (max_duration is not None and n / float(sr) > max_duration):
+                continue
+            by_sr.setdefault(int(sr), []).append(i)
+        for sr, idxs in by_sr.items():
+            groups = {}
+            for i in idxs:                                   # int16 and float signals are collated separately
+                groups.setdefault(np.asarray(signals[i]).dtype == np.int16, []).append(i)
+            for _, gi in groups.items():
+                lens = [int(np.asarray(signals[i]).shape[0]) for i in gi]
+                for batch in audio.plan_batches(lens, batch_size, int(max_padded_seconds * sr)):
+                    ids = [gi[j] for j in batch]
+                    w, ln = audio.collate([signals[i] for i in ids])
+                    w, ln = w.cuda(non_blocking=True), ln.cuda(non_blocking=True)
+                    w, ln = self._resampler(w, ln, sr, self.sample_rate)
+                    if kind == "greedy":
+                        texts = self.transcribe_batch_device(w, ln)
+                    else:
+                        texts = self.beam_batch_device(w, ln)
+                    for i, t in zip(ids, texts):
+                        out[i] = t
+        return out
+
+    def transcribe_files(self, paths: Sequence[str], **kwargs) -> List[Optional[str]]:
+        """WAV files -> transcripts (see `transcribe_signals`)."""
+        sigs, srs = [], []
+        for p in paths:
+            a, sr = audio.read_wav(p)
+            sigs.append(a); srs.append(sr)
+        return self.transcribe_signals(sigs, srs, **kwargs)
 
     def transcribe(self, audio_signal: np.ndarray) -> str:
         """infer.py:167-171: one utterance -> text (beam search, LM-fused when `lm_path` was given; greedy when the
