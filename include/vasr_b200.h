@@ -213,8 +213,10 @@ int64_t vasr_resample_out_len(int64_t n_in, int sr_in, int sr_out);
 /* pcm [B, L] i16, length [B] i64 -> wave [B, L] f32 (zero beyond length)                                         */
 int  vasr_pcm16_to_float(const int16_t* pcm, const int64_t* length, int B, int64_t L, float* wave, void* stream);
 /* x [B, L_in] (f32, or i16 PCM when pcm16 != 0), len_in [B] i64 -> y [B, L_out] f32 (zero beyond len_out),
- * len_out [B] i64; L_out >= vasr_resample_out_len(L_in, sr_in, sr_out).  All device pointers.                    */
-int  vasr_resample(const vasr_resampler* rs, const void* x, int pcm16, const int64_t* len_in, int B, int64_t L_in,
+ * len_out [B] i64; L_out >= vasr_resample_out_len(L_in, sr_in, sr_out).  All device pointers.  The handle caches
+ * resampy's running-sum time table per ratio (rebuilt on the stream when the ratio changes or L_out grows): one
+ * handle per caller thread.                                                                                       */
+int  vasr_resample(vasr_resampler* rs, const void* x, int pcm16, const int64_t* len_in, int B, int64_t L_in,
                    int sr_in, int sr_out, float* y, int64_t* len_out, int64_t L_out, void* stream);
 
 /* ---- whole path, HOST buffers (the reference-facing plugin call) ------- */

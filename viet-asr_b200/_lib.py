@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvasr_b200.so")
+# VASR_B200_LIB: developer override to time an experimental build of the same library (tools/); never a fallback
+LIB_PATH = os.environ.get("VASR_B200_LIB") or os.path.join(_HERE, "libvasr_b200.so")
 
 VASR_OK, VASR_EINVAL, VASR_ECUDA, VASR_ESTATE, VASR_ENOMEM = 0, -1, -2, -3, -4
 GEMM_FP32_SIMT, GEMM_F16X3, GEMM_F16X1 = 0, 1, 2

@@ -8,8 +8,12 @@
 //          int(n * ratio), then librosa's fix_length to ceil(n * ratio) (zero padded).
 // librosa / resampy are un-vendored third-party packages that are absent from this image: the algorithm is restated
 // from the published one (oracle/resample_oracle.py is the scalar restatement used by the tests) - parity with the
-// packages themselves is UNPINNED.  Deviation: the input time of output sample t is t * (1/ratio) in fp64 here,
-// resampy accumulates `time += 1/ratio`; identical for exactly representable increments (8 kHz -> 16 kHz: 0.5).
+// packages themselves is UNPINNED.  resampy 0.2.x (the release of the reference's era) advances the input time of
+// successive output samples by a running fp64 sum `time_register += 1/ratio`; because its filter-table stride is
+// truncated to an integer (int(scale * num_table)) the interpolator is not continuous where the time crosses an
+// integer, so the rounding of that running sum is observable for ratios whose increment is not a dyadic fraction
+// (44.1 kHz -> 16 kHz).  The sum is therefore reproduced exactly: `time_table_kernel` (one thread, sequential fp64
+// adds, once per ratio / length, cached in the handle) writes time_register[t], the resampling kernel reads it.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -18,6 +22,9 @@ struct vasr_resampler {
     float* d_delta = nullptr;   // [n_win] forward differences (last = 0)
     int n_win = 0;
     int num_table = 0;          // table entries per zero crossing
+    double* d_time = nullptr;   // [time_cap] resampy's running sum time_register[t] for time_inc
+    long long time_cap = 0;
+    double time_inc = 0.0;
 };
 
 namespace vasr {
@@ -41,12 +48,24 @@ template <> __device__ __forceinline__ float load_sample<int16_t>(const int16_t*
     return (float)__ldg(x + i) * (1.0f / 32768.0f);
 }
 
+// time_register[0] = 0, time_register[t] = time_register[t-1] + inc: the exact sequence of fp64 roundings of resampy's
+// sample loop (interpn.resample_f).  Sequential by construction; the same table serves every utterance of a batch.
+__global__ void time_table_kernel(double* __restrict__ tbl, long long n, double inc)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double t = 0.0;
+    for (long long i = 0; i < n; ++i) {
+        tbl[i] = t;
+        t = __dadd_rn(t, inc);
+    }
+}
+
 // one thread per output sample: left wing (x[n], x[n-1], ...) + right wing (x[n+1], ...) of the interpolation filter
 template <typename TIn>
 __global__ void resample_kernel(const TIn* __restrict__ x, const long long* __restrict__ len_in, long long L_in,
                                 float* __restrict__ y, long long* __restrict__ len_out, long long L_out,
-                                double ratio, const float* __restrict__ win, const float* __restrict__ delta,
-                                int n_win, int num_table, float gain)
+                                double ratio, const double* __restrict__ time_tbl, const float* __restrict__ win,
+                                const float* __restrict__ delta, int n_win, int num_table, float gain)
 {
     const int b = blockIdx.y;
     const long long n_orig = len_in[b];
@@ -57,12 +76,11 @@ __global__ void resample_kernel(const TIn* __restrict__ x, const long long* __re
     const TIn* xr = x + (size_t)b * L_in;
     float* yr = y + (size_t)b * L_out;
     const double scale = ratio < 1.0 ? ratio : 1.0;
-    const double time_increment = 1.0 / ratio;
     const int index_step = (int)(scale * num_table);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < L_out; t += (long long)gridDim.x * blockDim.x) {
         float acc = 0.f;
         if (t < n_res) {
-            const double time_register = (double)t * time_increment;
+            const double time_register = time_tbl[t];
             const long long n = (long long)time_register;
             // left wing
             double frac = scale * (time_register - (double)n);
@@ -121,7 +139,7 @@ extern "C" int vasr_resampler_create(const float* interp_win_host, int n_win, in
 extern "C" void vasr_resampler_destroy(vasr_resampler* rs)
 {
     if (!rs) return;
-    cudaFree(rs->d_win); cudaFree(rs->d_delta);
+    cudaFree(rs->d_win); cudaFree(rs->d_delta); cudaFree(rs->d_time);
     delete rs;
 }
 
@@ -142,7 +160,7 @@ extern "C" int vasr_pcm16_to_float(const int16_t* pcm, const int64_t* length, in
     return VASR_OK;
 }
 
-extern "C" int vasr_resample(const vasr_resampler* rs, const void* x, int pcm16, const int64_t* len_in, int B, int64_t L_in,
+extern "C" int vasr_resample(vasr_resampler* rs, const void* x, int pcm16, const int64_t* len_in, int B, int64_t L_in,
                              int sr_in, int sr_out, float* y, int64_t* len_out, int64_t L_out, void* stream)
 {
     using namespace vasr;
@@ -159,14 +177,27 @@ extern "C" int vasr_resample(const vasr_resampler* rs, const void* x, int pcm16,
     const float gain = ratio < 1.0 ? (float)ratio : 1.0f;
     dim3 grid((unsigned)std::min<int64_t>(ceil_div64(L_out, 128), 2368), (unsigned)B);
     cudaStream_t st = (cudaStream_t)stream;
+    const double inc = 1.0 / ratio;
+    if (rs->time_inc != inc || rs->time_cap < L_out) {
+        // (re)build the time table on this stream; the old table may still be read by earlier launches: cudaFree
+        // synchronises the device before releasing it
+        const long long cap = std::max<long long>((long long)L_out, rs->time_inc == inc ? 2 * rs->time_cap : 0);
+        double* t = nullptr;
+        cudaError_t e = cudaMalloc(&t, sizeof(double) * (size_t)cap);
+        if (e != cudaSuccess) return set_error(VASR_ECUDA, "vasr_resample: time table (%lld entries): %s", cap, cudaGetErrorString(e));
+        cudaFree(rs->d_time);
+        rs->d_time = t; rs->time_cap = cap; rs->time_inc = inc;
+        time_table_kernel<<<1, 32, 0, st>>>(rs->d_time, cap, inc);
+        VASR_LAUNCH_OK("time_table_kernel");
+    }
     if (pcm16)
         resample_kernel<int16_t><<<grid, 128, 0, st>>>((const int16_t*)x, (const long long*)len_in, (long long)L_in, y,
-                                                      (long long*)len_out, (long long)L_out, ratio, rs->d_win, rs->d_delta,
-                                                      rs->n_win, rs->num_table, gain);
+                                                      (long long*)len_out, (long long)L_out, ratio, rs->d_time, rs->d_win,
+                                                      rs->d_delta, rs->n_win, rs->num_table, gain);
     else
         resample_kernel<float><<<grid, 128, 0, st>>>((const float*)x, (const long long*)len_in, (long long)L_in, y,
-                                                    (long long*)len_out, (long long)L_out, ratio, rs->d_win, rs->d_delta,
-                                                    rs->n_win, rs->num_table, gain);
+                                                    (long long*)len_out, (long long)L_out, ratio, rs->d_time, rs->d_win,
+                                                    rs->d_delta, rs->n_win, rs->num_table, gain);
     VASR_LAUNCH_OK("resample_kernel");
     return VASR_OK;
 }

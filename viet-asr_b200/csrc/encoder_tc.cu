@@ -23,6 +23,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace vasr {
 namespace tc {
@@ -62,18 +63,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+// tight spin: only for the depthwise warps, which own the critical resource (the FP32 pipe) and wait rarely
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
+    while (!mbar_try(bar, parity)) {}
+}
+// wait with back-off for the roles that spend most of their time waiting (producers, MMA issuer, epilogue):
+// try_wait returns after a few cycles, so a tight loop of 11 waiting warps issues ~0.6 instructions per clock per
+// scheduler (ncu: SYNCS + BRA + YIELD = 62 % of all instructions of the segment kernel) and takes issue slots away
+// from the one depthwise warp on the same scheduler.  nanosleep parks the warp instead.
+__device__ __forceinline__ void mbar_wait_bo(uint64_t* bar, uint32_t parity, uint32_t ns)
+{
+    if (mbar_try(bar, parity)) return;
+    if (ns == 0) { while (!mbar_try(bar, parity)) {} return; }
+    do { __nanosleep(ns); } while (!mbar_try(bar, parity));
 }
 __device__ __forceinline__ void fence_barrier_init()
 {
@@ -189,30 +203,81 @@ struct Params {
     unsigned long long* prof; // optional [16] cycle counters (VASR_TC_PROF=1), see tools/
     int tma_epi;              // 1: epilogue stages 128 x 32 output slices in smem and stores them with TMA
     int dbg;                  // timing experiments only (VASR_TC_DBG): 1 = skip MMAs, 2 = skip depthwise FMAs, 4 = skip epilogue stores
+    int spin[4];              // back-off (ns) of the waiting roles: window producer, weight producer, MMA issuer, epilogue
 };
 
 // Depthwise FIR of one chunk for one thread: channel pair `xs`/`wp` (already offset by the pair), R consecutive outputs
 // starting at window row tw.  Rolling register window, fully unrolled over the taps: window slot of (output r, tap k)
 // holds row tw + r + k*D.  Each tap consumes R FFMA2 and refills D rows + 1 tap weight that are needed P taps later,
 // so shared-memory loads are spread evenly between the FMAs and only R + D*P rows are live.
+// Depthwise tap storage of one 32-channel chunk.  VASR_DW_TAP128 = 1: taps are stored in pairs,
+// [ceil(K/2)][16 channel pairs][tap 2j: ch0 ch1 | tap 2j+1: ch0 ch1], so that one 16-byte shared-memory load feeds two
+// taps of a thread's channel pair (1.5 loads per tap instead of 2: fewer loads in flight per scoreboard).
+// VASR_DW_TAP128 = 0: [K][32 channels], one 8-byte load per tap.
+#ifndef VASR_DW_TAP128
+#define VASR_DW_TAP128 0
+#endif
+__host__ __device__ constexpr int tap_floats(int K) { return VASR_DW_TAP128 ? ((K + 1) / 2) * 2 * KC : K * KC; }
+// tap k of the channel pair whose taps start at `wp` (already offset by the pair)
+__device__ __forceinline__ float2 tap_load(const float2* __restrict__ wp, int k)
+{
+#if VASR_DW_TAP128
+    return wp[(size_t)(k >> 1) * KC + (k & 1)];               // pair stride: 16 pairs x 4 floats = KC float2
+#else
+    return wp[(size_t)k * (KC / 2)];
+#endif
+}
+__device__ __forceinline__ const float2* tap_base(const void* taps, int cp)
+{
+#if VASR_DW_TAP128
+    return reinterpret_cast<const float2*>(taps) + 2 * cp;
+#else
+    return reinterpret_cast<const float2*>(taps) + cp;
+#endif
+}
+
 template <int K, int D, int R>
 __device__ __forceinline__ void dw_chunk_s1(const float2* __restrict__ xs, const float2* __restrict__ wp, int tw, float2 (&acc)[R])
 {
-    constexpr int XP = KC / 2, wstride = KC / 2;
-    constexpr int P = 4;
+    constexpr int XP = KC / 2;
+    // prefetch distance in taps.  Every tap issues two shared-memory loads and a consumer waits on the scoreboard of
+    // its load; with 2P + 1 loads in flight and 6 scoreboards per warp, P > 2 makes loads share scoreboards, so a
+    // consumer also waits for younger loads and the effective distance shrinks (profiles/: stall_short_sb)
+#ifndef VASR_DW_PREFETCH
+#define VASR_DW_PREFETCH 4
+#endif
+    constexpr int P = VASR_DW_PREFETCH;
     constexpr int WN = R + D * P;
     constexpr int LAST_ROW = (K - 1) * D + R - 1;
-    float2 win[WN], wq[P];
+    float2 win[WN];
 #pragma unroll
     for (int j = 0; j < WN; ++j) win[j] = (j <= LAST_ROW) ? xs[(size_t)(tw + j) * XP] : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < P; ++j) wq[j] = (j < K) ? wp[(size_t)j * wstride] : make_float2(0.f, 0.f);
-#pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+#if VASR_DW_TAP128
+    constexpr int K2 = (K + 1) / 2;
+#ifndef VASR_DW_TAPPAIRS
+#define VASR_DW_TAPPAIRS 2
+#endif
+    constexpr int PW = VASR_DW_TAPPAIRS;                       // tap pairs in flight
+    const float4* wp4 = reinterpret_cast<const float4*>(wp);
+    float4 wq[PW];
+#pragma unroll
+    for (int j = 0; j < PW; ++j) wq[j] = (j < K2) ? wp4[(size_t)j * (KC / 2)] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float4 w4 = wq[(k >> 1) % PW];
+        const float2 wk = (k & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
+        if (((k & 1) || k + 1 == K) && (k >> 1) + PW < K2) wq[(k >> 1) % PW] = wp4[(size_t)((k >> 1) + PW) * (KC / 2)];
+#else
+    float2 wq[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) wq[j] = (j < K) ? tap_load(wp, j) : make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float2 wk = wq[k % P];
-        if (k + P < K) wq[k % P] = wp[(size_t)(k + P) * wstride];
+        if (k + P < K) wq[k % P] = tap_load(wp, k + P);
+#endif
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = __ffma2_rn(wk, win[(k * D + r) % WN], acc[r]);
 #pragma unroll
@@ -319,7 +384,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int gc = 0;
             for (int ti = 0;; ++ti) {
                 const int slot = ti % SCHED;
-                mbar_wait(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
+                mbar_wait_bo(sched_empty + slot, ((ti / SCHED) & 1) ^ 1, (uint32_t)p.spin[0]);
                 int tile = atomicAdd(p.tile_counter, 1);
                 if (tile >= n_tiles) tile = -1;
                 tile_ring[slot] = tile;
@@ -330,16 +395,16 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int s = gc % XSTAGES;
                     PROF_BEGIN();
-                    mbar_wait(empty_x + s, ((gc / XSTAGES) & 1) ^ 1);
+                    mbar_wait_bo(empty_x + s, ((gc / XSTAGES) & 1) ^ 1, (uint32_t)p.spin[0]);
                     PROF_ADD(0);
                     unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
                     if (c < p.n_main) {
-                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(p.n_xbox * p.xbox_rows * KC * 4 + K * KC * 4));
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(p.n_xbox * p.xbox_rows * KC * 4 + tap_floats(K) * 4));
                         for (int j = 0; j < p.n_xbox; ++j)
                             tma_load_3d(dst + (size_t)j * p.xbox_rows * KC * 4, &tm_x, c * KC,
                                         t0 * S - p.pad + j * p.xbox_rows, b, full_x + s);
                         // the chunk's depthwise taps [K][32] ride in the same stage (no exposed global-load latency)
-                        bulk_load(dst + p.x_w_off, p.dw_w + (size_t)c * K * KC, (uint32_t)(K * KC * 4), full_x + s);
+                        bulk_load(dst + p.x_w_off, p.dw_w + (size_t)c * tap_floats(K), (uint32_t)(tap_floats(K) * 4), full_x + s);
                     } else {
                         mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
                         tma_load_3d(dst, &tm_r, (c - p.n_main) * KC, t0, b, full_x + s);
@@ -361,7 +426,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const int ci0 = (res ? c - p.n_main : c) * KC;
                     for (int m = 0; m < p.nN; ++m) {
                         PROF_BEGIN();
-                        mbar_wait(empty_a + slot, ph ^ 1);
+                        mbar_wait_bo(empty_a + slot, ph ^ 1, (uint32_t)p.spin[1]);
                         PROF_ADD(0);
                         mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
@@ -383,17 +448,17 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (lane == 0) {
                 const int ab = ti % nbuf;
                 PROF_BEGIN();
-                mbar_wait(acc_empty + ab, ((ti / nbuf) & 1) ^ 1);     // epilogue has drained this accumulator buffer
+                mbar_wait_bo(acc_empty + ab, ((ti / nbuf) & 1) ^ 1, (uint32_t)p.spin[2]);     // epilogue has drained this accumulator buffer
                 PROF_ADD(2);
                 tcgen05_fence_after();
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int sb = gc % BSTAGES;
-                    mbar_wait(full_b + sb, (gc / BSTAGES) & 1);
+                    mbar_wait_bo(full_b + sb, (gc / BSTAGES) & 1, (uint32_t)p.spin[2]);
                     PROF_ADD(0);
                     tcgen05_fence_after();
                     const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
                     for (int m = 0; m < p.nN; ++m) {
-                        mbar_wait(full_a + slot, ph);
+                        mbar_wait_bo(full_a + slot, ph, (uint32_t)p.spin[2]);
                         PROF_ADD(1);
                         tcgen05_fence_after();
                         const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
@@ -454,14 +519,21 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
             // +shift (BN), ReLU, length mask on one 32-channel slice held in registers, then out
             auto finish = [&](uint32_t (&rg)[32], int col0) {
+                // hoisted above the staging stores (see segment_kernel) where the register budget allows it (4 dw warps)
+                constexpr bool HOIST = (NDW == 4);
                 const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                float4 shv[HOIST ? 8 : 1];
+                if (HOIST) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) shv[HOIST ? i : 0] = sh4[i];
+                }
                 if (p.tma_epi) {
                     if (issuer) bulk_wait_read0();             // previous slice has left the staging buffer
                     named_bar_sync(1 + half, 128);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 sh = sh4[i];                   // shared-memory broadcast (same address in every lane)
+                    const float4 sh = HOIST ? shv[HOIST ? i : 0] : sh4[i];
                     float4 v;
                     v.x = fmaf(__uint_as_float(rg[4 * i + 0]), wsc, sh.x);
                     v.y = fmaf(__uint_as_float(rg[4 * i + 1]), wsc, sh.y);
@@ -481,7 +553,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 }
             };
             PROF_BEGIN();
-            mbar_wait(acc_full + ab, (ti / nbuf) & 1);
+            mbar_wait_bo(acc_full + ab, (ti / nbuf) & 1, (uint32_t)p.spin[3]);
             PROF_ADD(0);
             tcgen05_fence_after();
             // one 32-column slice in registers at a time: with 608 threads the register budget (<= 104) does not
@@ -535,8 +607,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
                 } else if (c < p.n_main) {
                     // depthwise taps of this chunk [K][32 ch], staged in shared memory next to the window
-                    const float2* wp = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes + p.x_w_off) + cp;
-                    constexpr int wstride = KC / 2;
+                    const float2* wp = tap_base(x_ring + (size_t)sx * p.x_stage_bytes + p.x_w_off, cp);
                     if (S == 1) {
                         dw_chunk_s1<K, D, R>(xs, wp, tw, acc);
                     } else {
@@ -554,7 +625,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                                 for (int j = 0; j < WIN; ++j) win[j] = xs[(size_t)((tw + 8 * h) * S + kb + j) * XP];
 #pragma unroll
                                 for (int kk = 0; kk < KB; ++kk) {
-                                    const float2 wk = wp[(size_t)(kb + kk) * wstride];
+                                    const float2 wk = tap_load(wp, kb + kk);
 #pragma unroll
                                     for (int r = 0; r < 8; ++r) acc[8 * h + r] = __ffma2_rn(wk, win[r * S + kk], acc[8 * h + r]);
                                 }
@@ -575,10 +646,15 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 mbar_wait(empty_b + sb, ((gc / BSTAGES) & 1) ^ 1);
                 PROF_ADD(2);
                 unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
+                // sw64_offset(tw + r, cp >> 2) with tw a multiple of 8: everything but the XOR-ed 16-byte chunk is a
+                // compile-time function of r -> four base pointers per chunk, immediate offsets per row
+                unsigned char* bq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bq[q] = bh + (tw >> 3) * 512 + (cp & 3) * 4 + ((((uint32_t)cp >> 2) ^ (uint32_t)q) << 4);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int row = tw + r;
-                    const uint32_t off = sw64_offset(row, cp >> 2) + (cp & 3) * 4;
+                    const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+                    unsigned char* bh = bq[(r >> 1) & 3];
                     const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
                     *reinterpret_cast<__half2*>(bh + off) = h;
                     if (NPART == 2) {
@@ -642,6 +718,7 @@ struct SegParams {
     int b0, n_tt, n_utt;
     unsigned long long* prof;
     int dbg;
+    int spin[4];             // back-off (ns) of the waiting roles: window producer, weight producer, MMA issuer, epilogue
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -739,7 +816,7 @@ segment_kernel(const SegParams p)
             int s = 0; uint32_t xph = 0;
             for (int ti = 0;; ++ti) {
                 const int slot = ti % SCHED;
-                mbar_wait(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
+                mbar_wait_bo(sched_empty + slot, ((ti / SCHED) & 1) ^ 1, (uint32_t)p.spin[0]);
                 int tile = atomicAdd(p.tile_counter, 1);
                 if (tile >= n_items) tile = -1;
                 tile_ring[slot] = tile;
@@ -762,14 +839,16 @@ segment_kernel(const SegParams p)
                 const float* dw_w = L->dw_w;
                 for (int c = 0; c < nch; ++c) {
                     PROF_BEGIN();
-                    mbar_wait(empty_x + s, xph ^ 1);
+                    mbar_wait_bo(empty_x + s, xph ^ 1, (uint32_t)p.spin[0]);
                     PROF_ADD(0);
                     unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
-                    if (c < n_main) {
-                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + K * KC * 4));
+                    if (p.dbg & 16) {
+                        mbar_arrive(full_x + s);
+                    } else if (c < n_main) {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + tap_floats(K) * 4));
                         for (int j = 0; j < n_xbox; ++j)
                             tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + s);
-                        bulk_load(dst + x_w_off, dw_w + (size_t)c * K * KC, (uint32_t)(K * KC * 4), full_x + s);
+                        bulk_load(dst + x_w_off, dw_w + (size_t)c * tap_floats(K), (uint32_t)(tap_floats(K) * 4), full_x + s);
                     } else {
                         mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
                         tma_load_3d(dst, &L->tm_r, (c - n_main) * KC, t0, b, full_x + s);
@@ -794,12 +873,16 @@ segment_kernel(const SegParams p)
                     const int ci0 = (res ? c - n_main : c) * KC;
                     for (int m = 0; m < p.nN; ++m) {
                         PROF_BEGIN();
-                        mbar_wait(empty_a + slot, ph ^ 1);
+                        mbar_wait_bo(empty_a + slot, ph ^ 1, (uint32_t)p.spin[1]);
                         PROF_ADD(0);
-                        mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
-                        tma_load_2d(dst, res ? &L->tm_r_hi : &L->tm_w_hi, ci0, m * 256, full_a + slot);
-                        if (NPART == 2) tma_load_2d(dst + W_PART, res ? &L->tm_r_lo : &L->tm_w_lo, ci0, m * 256, full_a + slot);
+                        if (p.dbg & 8) {
+                            mbar_arrive(full_a + slot);
+                        } else {
+                            mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
+                            tma_load_2d(dst, res ? &L->tm_r_hi : &L->tm_w_hi, ci0, m * 256, full_a + slot);
+                            if (NPART == 2) tma_load_2d(dst + W_PART, res ? &L->tm_r_lo : &L->tm_w_lo, ci0, m * 256, full_a + slot);
+                        }
                         if (++slot == p.aslots) { slot = 0; ph ^= 1; }
                     }
                 }
@@ -819,16 +902,16 @@ segment_kernel(const SegParams p)
                 decode(tile, l, b, t0);
                 const int nch = p.layers[l].n_main + p.layers[l].n_res;
                 PROF_BEGIN();
-                mbar_wait(acc_empty + ab, accph ^ 1);
+                mbar_wait_bo(acc_empty + ab, accph ^ 1, (uint32_t)p.spin[2]);
                 PROF_ADD(2);
                 tcgen05_fence_after();
                 for (int c = 0; c < nch; ++c) {
-                    mbar_wait(full_b + sb, bph);
+                    mbar_wait_bo(full_b + sb, bph, (uint32_t)p.spin[2]);
                     PROF_ADD(0);
                     tcgen05_fence_after();
                     const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
                     for (int m = 0; m < p.nN; ++m) {
-                        mbar_wait(full_a + slot, ph);
+                        mbar_wait_bo(full_a + slot, ph, (uint32_t)p.spin[2]);
                         PROF_ADD(1);
                         tcgen05_fence_after();
                         const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
@@ -837,6 +920,7 @@ segment_kernel(const SegParams p)
                         for (int ks = 0; ks < KC / 16; ++ks) {
                             const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
                             const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                            if (p.dbg & 1) continue;
                             umma_f16(d, x_hi, w_hi, IDESC_F16_M128_N256, (c > 0 || ks > 0) ? 1u : 0u);
                             if (NPART == 2) {
                                 const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
@@ -887,7 +971,7 @@ segment_kernel(const SegParams p)
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
             auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
             PROF_BEGIN();
-            mbar_wait(acc_full + ab, accph);
+            mbar_wait_bo(acc_full + ab, accph, (uint32_t)p.spin[3]);
             PROF_ADD(0);
             tcgen05_fence_after();
             const int ab_cur = ab;
@@ -897,18 +981,26 @@ segment_kernel(const SegParams p)
             for (int sidx = 0; sidx < nslice; ++sidx) {
                 const int col0 = slice_col(sidx);
                 tmem_ld_32x32b_x32(tbase + (uint32_t)col0, ra);
+                // the slice's BN shift (shared-memory broadcast) is fetched while the TMEM load is in flight; loading it
+                // inside the loop below would chain every LDS behind the previous staging STS (possible alias) and
+                // expose its latency eight times per slice
+                float4 shv[8];
+                {
+                    const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) shv[i] = sh4[i];
+                }
                 tmem_ld_wait();
                 if (sidx + 1 == nslice) {                      // every TMEM read of this tile has completed
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + ab_cur);
                 }
-                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
                 if (issuer) bulk_wait_read0();                 // previous slice has left the staging buffer
                 named_bar_sync(1 + half, 128);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 sh = sh4[i];
+                    const float4 sh = shv[i];
                     float4 v;
                     v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, sh.x);
                     v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, sh.y);
@@ -916,11 +1008,11 @@ segment_kernel(const SegParams p)
                     v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, sh.w);
                     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
+                    if (!(p.dbg & 32)) *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
                 }
                 fence_proxy_async();
                 named_bar_sync(1 + half, 128);
-                if (issuer) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
+                if (issuer && !(p.dbg & 4)) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
             }
             if (issuer) {
                 // this half's part of the tile is in global memory: publish it to the tiles of the next layer
@@ -954,7 +1046,7 @@ segment_kernel(const SegParams p)
                 const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
                 float2 acc[R];
                 if (c < n_main) {
-                    const float2* wp = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes + x_w_off) + cp;
+                    const float2* wp = tap_base(x_ring + (size_t)sx * p.x_stage_bytes + x_w_off, cp);
                     SEG_K_SWITCH(K, (dw_chunk_s1<KK, 1, R>(xs, wp, tw, acc)));
                 } else {
 #pragma unroll
@@ -968,11 +1060,15 @@ segment_kernel(const SegParams p)
                 PROF_ADD(1);
                 mbar_wait(empty_b + sb, bph ^ 1);
                 PROF_ADD(2);
-                unsigned char* bh = b_ring + (size_t)sb * B_STAGE;
+                unsigned char* bh0 = b_ring + (size_t)sb * B_STAGE;
+                unsigned char* bq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bq[q] = bh0 + (tw >> 3) * 512 + (cp & 3) * 4 + ((((uint32_t)cp >> 2) ^ (uint32_t)q) << 4);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const int row = tw + r;
-                    const uint32_t off = sw64_offset(row, cp >> 2) + (cp & 3) * 4;
+                    if (p.dbg & 64) break;
+                    const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+                    unsigned char* bh = bq[(r >> 1) & 3];
                     const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
                     *reinterpret_cast<__half2*>(bh + off) = h;
                     if (NPART == 2) {
@@ -1059,6 +1155,20 @@ static const KernelEntry* find_kernel(int K, int S, int D)
 }
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+// back-off of the waiting roles in ns (window producer, weight producer, MMA issuer, epilogue); VASR_TC_SPIN=a,b,c,d
+// overrides (0 = tight spin).  Defaults from the sweep in profiles/.
+static void spin_defaults(int (&spin)[4])
+{
+    static int v[4] = {-1, 0, 0, 0};
+    if (v[0] < 0) {
+        int d[4] = {200, 50, 50, 100};
+        const char* e = getenv("VASR_TC_SPIN");
+        if (e) sscanf(e, "%d,%d,%d,%d", &d[0], &d[1], &d[2], &d[3]);
+        for (int i = 0; i < 4; ++i) v[i] = d[i] < 0 ? 0 : d[i];
+    }
+    for (int i = 0; i < 4; ++i) spin[i] = v[i];
+}
+
 static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_off, int* stage_bytes)
 {
     const int rows = (TN - 1) * S + (K - 1) * D + 1;
@@ -1067,7 +1177,7 @@ static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_
     int bytes = nb * br * KC * 4;
     if (bytes < TN * KC * 4) bytes = TN * KC * 4;            // residual / identity chunks load 128 rows
     *n_xbox = nb; *xbox_rows = br; *w_off = bytes;
-    bytes += K * KC * 4;                                      // + the chunk's depthwise taps
+    bytes += tap_floats(K) * 4;                               // + the chunk's depthwise taps
     *stage_bytes = (bytes + 1023) / 1024 * 1024;
 }
 
@@ -1176,13 +1286,21 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
         memcpy(sb.tm_r_hi, sb.tm_w_hi, sizeof(sb.tm_w_hi));
         memcpy(sb.tm_r_lo, sb.tm_w_lo, sizeof(sb.tm_w_lo));
     }
-    {   // depthwise taps re-packed per 32-channel chunk: [Cin/32][K][32]; identity for a plain 1x1 conv
+    {   // depthwise taps re-packed per 32-channel chunk (layout: tap_floats / tap_load); identity for a plain 1x1 conv
         const int K = sb.separable ? sb.kernel : 1;
-        std::vector<float> pk((size_t)Ci * K, 1.0f);
-        if (sb.separable)
-            for (int c = 0; c < Ci; ++c)
-                for (int k = 0; k < K; ++k)
-                    pk[((size_t)(c / KC) * K + k) * KC + (c % KC)] = dw_kc[(size_t)k * Ci + c];
+        const int per_chunk = tap_floats(K);
+        std::vector<float> pk((size_t)(Ci / KC) * per_chunk, 0.0f);
+        for (int c = 0; c < Ci; ++c)
+            for (int k = 0; k < K; ++k) {
+                const float v = sb.separable ? dw_kc[(size_t)k * Ci + c] : 1.0f;
+                const int cc = c % KC;
+#if VASR_DW_TAP128
+                const size_t idx = (size_t)(c / KC) * per_chunk + (size_t)(k >> 1) * 2 * KC + (cc >> 1) * 4 + (k & 1) * 2 + (cc & 1);
+#else
+                const size_t idx = (size_t)(c / KC) * per_chunk + (size_t)k * KC + cc;
+#endif
+                pk[idx] = v;
+            }
         if ((rc = up(pk.data(), sizeof(float) * pk.size(), (void**)&sb.dw_tc))) return rc;
     }
     return VASR_OK;
@@ -1254,6 +1372,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
         if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
     }
     p.prof = prof_on ? d_prof : nullptr;
+    spin_defaults(p.spin);
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     // depthwise warps per CTA: 4 (16 outputs per thread) by default, VASR_TC_NDW=8 selects the 8-warp variant
@@ -1377,7 +1496,8 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
         if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
     }
     p.prof = prof_on ? d_prof : nullptr;
-    p.dbg = 0;
+    spin_defaults(p.spin);
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     void* args[] = {(void*)&p};
     const void* fn = split3 ? (const void*)segment_kernel<2, 4> : (const void*)segment_kernel<1, 4>;
