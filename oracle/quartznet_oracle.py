@@ -108,6 +108,29 @@ def normalize_batch(x: torch.Tensor, seq_len: torch.Tensor) -> torch.Tensor:
     return (x - x_mean.unsqueeze(2)) / x_std.unsqueeze(2)
 
 
+def conv_stft_magnitude(x: torch.Tensor, n_fft: int, hop: int, win_length: int, window: str) -> torch.Tensor:
+    """`torch_stft.STFT(n_fft, hop, win_length, window).transform(x)[0]` - what `stft_conv: true` selects
+    (features.py:156-167; quartznet15x5.yaml:26).  torch_stft is an un-vendored third-party package that is absent
+    from the image: restated from its published algorithm, parity with the package UNPINNED.  Algorithm: Fourier basis
+    rows [cos; -sin] of the first n_fft/2+1 bins, multiplied by `scipy.signal.get_window(window, win_length,
+    fftbins=True)` (a PERIODIC window, unlike the symmetric one of the torch path) zero-padded to n_fft around the
+    centre; the signal is reflect-padded by n_fft/2 and correlated with the basis at stride `hop` (conv1d);
+    magnitude = sqrt(re^2 + im^2)."""
+    from scipy.signal import get_window
+    import numpy as np
+    cutoff = n_fft // 2 + 1
+    basis = np.fft.fft(np.eye(n_fft))
+    basis = np.vstack([np.real(basis[:cutoff, :]), np.imag(basis[:cutoff, :])])
+    win = get_window(window, win_length, fftbins=True)
+    lpad = (n_fft - win_length) // 2
+    win = np.pad(win, (lpad, n_fft - win_length - lpad))
+    fwd = torch.from_numpy((basis * win[None, :]).astype(np.float32))[:, None, :]
+    xp = F.pad(x.unsqueeze(1).unsqueeze(1), (n_fft // 2, n_fft // 2, 0, 0), mode="reflect").squeeze(1)
+    ft = F.conv1d(xp, fwd, stride=hop, padding=0)
+    re, im = ft[:, :cutoff, :], ft[:, cutoff:, :]
+    return torch.sqrt(re ** 2 + im ** 2)
+
+
 def filterbank_features(
     x: torch.Tensor,
     length: torch.Tensor,
@@ -120,6 +143,8 @@ def filterbank_features(
     log_zero_guard_value: float = 2 ** -24,
     pad_to: int = 0,
     return_pre_norm: bool = False,
+    window: str = "hann",
+    stft_conv: bool = False,
 ):
     """FilterbankFeatures.forward (features.py:245-301) with the settings that
     apply on the inference path: dither=0 and pad_to=0 (infer.py:89-90),
@@ -135,12 +160,17 @@ def filterbank_features(
     seq_len = get_seq_len(length, n_window_stride)  # :247
     # :255 preemphasis over the whole padded row
     x = torch.cat((x[:, 0].unsqueeze(1), x[:, 1:] - preemph * x[:, :-1]), dim=1)
-    window = torch.hann_window(n_window_size, periodic=False).to(torch.float)  # :179-180
-    spec = torch.stft(
-        x, n_fft=n_fft, hop_length=n_window_stride, win_length=n_window_size,
-        center=True, window=window, return_complex=True,
-    )  # :181-188, pad_mode='reflect' default
-    power = torch.view_as_real(spec).pow(2.0).sum(-1)  # :260-263
+    if stft_conv:
+        power = conv_stft_magnitude(x, n_fft, n_window_stride, n_window_size, window).pow(2.0)  # :156-167, :260-261
+    else:
+        window_fn = {"hann": torch.hann_window, "hamming": torch.hamming_window, "blackman": torch.blackman_window,
+                     "bartlett": torch.bartlett_window, "none": None}.get(window, None)  # :171-178
+        win = window_fn(n_window_size, periodic=False).to(torch.float) if window_fn else None  # :179-180
+        spec = torch.stft(
+            x, n_fft=n_fft, hop_length=n_window_stride, win_length=n_window_size,
+            center=True, window=win, return_complex=True,
+        )  # :181-188, pad_mode='reflect' default
+        power = torch.view_as_real(spec).pow(2.0).sum(-1)  # :260-263
     fb = torch.from_numpy(
         slaney_mel_filterbank(sample_rate, n_fft, nfilt, 0.0, sample_rate / 2)
     ).unsqueeze(0)  # :199-205

@@ -74,6 +74,26 @@ def test_frontend_pad_to_16_like_training_configs():
     assert (feats.cpu() - ref).abs().max().item() < FEAT_ATOL
 
 
+@pytest.mark.parametrize("window,stft_conv", [("hann", True), ("hamming", False), ("blackman", True), ("bartlett", False)])
+def test_frontend_windows_and_conv_stft(window, stft_conv):
+    """`stft_conv: true` (quartznet15x5.yaml:26 -> torch_stft convolution STFT, periodic window) and the other window
+    names of features.py:171-178 against the oracle restatement (oracle.conv_stft_magnitude: parity with torch_stft
+    itself unpinned)."""
+    V = _cuda()
+    V.NeuralModuleFactory(placement=V.DeviceType.GPU)
+    wave = (0.1 * torch.randn(3, 30000, generator=torch.Generator().manual_seed(17))).clamp_(-1, 1)
+    length = torch.tensor([30000, 21111, 1600])
+    for i in range(3):
+        wave[i, length[i]:] = 0
+    cfg = dict(V.configs.PREPROCESSOR_DEFAULT, window=window, stft_conv=stft_conv)
+    feats, seq = V.AudioToMelSpectrogramPreprocessor(**cfg).forward(input_signal=wave.cuda(), length=length.cuda())
+    ref, ref_seq = O.filterbank_features(wave, length, window=window, stft_conv=stft_conv)
+    assert seq.cpu().tolist() == ref_seq.tolist() and feats.shape == ref.shape
+    assert (feats.cpu() - ref).abs().max().item() < FEAT_ATOL
+    other, _ = O.filterbank_features(wave, length, window=window, stft_conv=not stft_conv)
+    assert (feats.cpu() - other).abs().max().item() > (feats.cpu() - ref).abs().max().item()   # it is the right window
+
+
 def test_frontend_real_audio_golden():
     V = _cuda()
     V.NeuralModuleFactory(placement=V.DeviceType.GPU)

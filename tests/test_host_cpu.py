@@ -72,8 +72,13 @@ def test_preprocessor_ctor_errors_like_reference():
         V.AudioToMelSpectrogramPreprocessor(dither=0, log_zero_guard_type="bogus")
     with pytest.raises(ValueError, match="dither"):
         V.AudioToMelSpectrogramPreprocessor()          # default dither 1e-5 is not the inference path
-    with pytest.raises(ValueError, match="stft_conv"):
-        V.AudioToMelSpectrogramPreprocessor(dither=0, stft_conv=True)
+    with pytest.raises(ValueError, match="window"):
+        V.AudioToMelSpectrogramPreprocessor(dither=0, window="none")
+    pc = V.AudioToMelSpectrogramPreprocessor(dither=0, stft_conv=True)      # quartznet15x5.yaml:26
+    from scipy.signal import get_window
+    np.testing.assert_allclose(pc._window.numpy(), get_window("hann", 320, fftbins=True), atol=1e-6)   # periodic
+    ps = V.AudioToMelSpectrogramPreprocessor(dither=0, window="hamming")
+    np.testing.assert_allclose(ps._window.numpy(), torch.hamming_window(320, periodic=False).numpy(), atol=0)
     p = V.AudioToMelSpectrogramPreprocessor(dither=0, pad_to=0, n_fft=512)
     assert p.num_frames(80000) == 501 and p.num_frames(69813) == 437
     p16 = V.AudioToMelSpectrogramPreprocessor(dither=0, pad_to=16, n_fft=512)

@@ -167,3 +167,18 @@ def test_beam_lm_oracle_properties():
     assert with_lm == "the cat sat"
     allb = BO.beam_search_lm(amb, labels, 16, lm, return_all=True)
     assert allb[0][2] == max(b[2] for b in allb)
+
+
+def test_conv_stft_restatement_equals_fft_with_periodic_window():
+    """`stft_conv: true` (features.py:156-167): the restated torch_stft convolution STFT (parity with the package
+    unpinned) must equal an FFT-based STFT with scipy's periodic window - the identity the CUDA front end relies on."""
+    g = torch.Generator().manual_seed(3)
+    x = 0.1 * torch.randn(2, 4000, generator=g)
+    for name, fn in (("hann", torch.hann_window), ("hamming", torch.hamming_window)):
+        mag = O.conv_stft_magnitude(x, 512, 160, 320, name)
+        ref = torch.stft(x, 512, 160, 320, window=fn(320, periodic=True), center=True, return_complex=True).abs()
+        assert mag.shape == ref.shape == (2, 257, 26)
+        assert (mag - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+    a, _ = O.filterbank_features(x, torch.tensor([4000, 3000]), stft_conv=True)
+    b, _ = O.filterbank_features(x, torch.tensor([4000, 3000]), stft_conv=False)
+    assert a.shape == b.shape and 1e-4 < (a - b).abs().max().item() < 0.5      # periodic vs symmetric window: close, not equal

@@ -70,13 +70,18 @@ def slaney_mel_filterbank(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: f
 
 
 # --------------------------------------------------------------------------- preprocessor
+_WINDOWS = {"hann": torch.hann_window, "hamming": torch.hamming_window, "blackman": torch.blackman_window,
+            "bartlett": torch.bartlett_window}   # features.py:171-178 ('none' dereferences a None window in the reference)
+
+
 class AudioToMelSpectrogramPreprocessor(NonTrainableNM):
     """audio_preprocessing.py:212-383 (wrapper) over FilterbankFeatures (parts/features.py:113-301).
 
-    Built configuration = what the shipped configs use on the inference path: window 'hann',
-    normalize 'per_feature', log with the 'add' guard, mag_power 2, frame_splicing 1,
-    stft_conv False, dither 0 (infer.py:89 forces 0; a non-zero dither is rejected rather
-    than silently ignored)."""
+    Built configuration = what the shipped configs use on the inference path: window 'hann' (also 'hamming',
+    'blackman', 'bartlett'), normalize 'per_feature', log with the 'add' guard, mag_power 2, frame_splicing 1,
+    stft_conv False (vi config) or True (quartznet15x5.yaml: the torch_stft convolution STFT = the same frames with
+    scipy's periodic window; parity with that un-vendored package is unpinned), dither 0 (infer.py:89 forces 0; a
+    non-zero dither is rejected rather than silently ignored)."""
 
     @property
     def input_ports(self):
@@ -111,13 +116,12 @@ class AudioToMelSpectrogramPreprocessor(NonTrainableNM):
             raise ValueError(f"{self} received {log_zero_guard_type} for the log_zero_guard_type parameter. "
                              f"It must be either 'add' or 'clamp'.")  # parts/features.py:216-221
         unsupported = []
-        if window != "hann": unsupported.append(f"window={window!r}")
+        if window not in _WINDOWS: unsupported.append(f"window={window!r}")
         if normalize != "per_feature": unsupported.append(f"normalize={normalize!r}")
         if not log or log_zero_guard_type != "add": unsupported.append("log/log_zero_guard_type")
         if isinstance(log_zero_guard_value, str): unsupported.append(f"log_zero_guard_value={log_zero_guard_value!r}")
         if mag_power != 2.0: unsupported.append(f"mag_power={mag_power}")
         if frame_splicing != 1: unsupported.append(f"frame_splicing={frame_splicing}")
-        if stft_conv: unsupported.append("stft_conv=True")
         if pad_value != 0: unsupported.append(f"pad_value={pad_value}")
         if dither and dither > 0: unsupported.append(f"dither={dither} (inference path uses 0, infer.py:89)")
         if pad_to == "max": unsupported.append("pad_to='max'")
@@ -130,7 +134,11 @@ class AudioToMelSpectrogramPreprocessor(NonTrainableNM):
         self.pad_to = int(pad_to)
         highfreq = highfreq or sample_rate / 2
         # constructor-time constants, computed exactly like the reference does
-        self._window = torch.hann_window(n_window_size, periodic=False).to(torch.float)  # features.py:179-180
+        # features.py:171-180: symmetric torch window; `stft_conv: true` (features.py:156-167, quartznet15x5.yaml:26)
+        # goes through torch_stft, whose basis is scaled by scipy's PERIODIC window (fftbins=True) - the same frames,
+        # reflect padding and power spectrum otherwise, so it is the same kernel with another window table
+        self.stft_conv = bool(stft_conv)
+        self._window = _WINDOWS[window](n_window_size, periodic=bool(stft_conv)).to(torch.float)
         self._fb = slaney_mel_filterbank(sample_rate, self.n_fft, features, lowfreq, highfreq)  # :199-205
         if self.n_fft != 512:
             raise ValueError(f"vasr_b200 AudioToMelSpectrogramPreprocessor: only n_fft=512 is built (got {self.n_fft})")
