@@ -740,11 +740,21 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
     }
 static bool seg_kernel_size(int K) { return K == 11 || K == 33 || K == 39 || K == 51 || K == 63 || K == 75; }
 
+// NDW = 4: one depthwise warp per scheduler, all four on the same chunk (480 threads).
+// NDW = 8 ("two groups"): warps 0-3 and 4-7 take alternate chunks, so every scheduler holds two depthwise warps whose
+// FMA streams fill each other's stalls and fp16-split/store phases.  20 warps (one idle, so that roles fall on
+// warpgroup boundaries): the kernel starts at 96 registers per thread and re-partitions them with setmaxnreg - 128
+// for the two depthwise warpgroups, 72 for everything else.  The increase can only be served from what the CTA's own
+// warps gave back (12 warps x 24 >= 8 warps x 32); the SM's unallocated registers are not in that pool (a first
+// version that counted on them - 136 / 80 - hung in USETMAXREG.TRY_ALLOC).
+__host__ __device__ constexpr int seg_threads(int ndw) { return ndw == 8 ? 640 : nthreads(ndw); }
 template <int NPART, int NDW>
-__global__ void __launch_bounds__(nthreads(NDW), 1)
+__global__ void __launch_bounds__(seg_threads(NDW), 1)
 segment_kernel(const SegParams p)
 {
-    constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = NDW + 3;
+    constexpr bool ALT = (NDW == 8);
+    constexpr int GW = 4;                                   // depthwise warps that share a chunk
+    constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = ALT ? 12 : NDW + 3;
     constexpr int SCHED_CONSUMERS = sched_consumers(NDW);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
@@ -778,8 +788,8 @@ segment_kernel(const SegParams p)
     const int nbuf = (acc_cols <= 256) ? 2 : 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, NDW); }
-        for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, NDW); mbar_init(empty_b + i, 1); }
+        for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, GW); }
+        for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, GW); mbar_init(empty_b + i, 1); }
         for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, NEPI); }
         for (int i = 0; i < SCHED; ++i) { mbar_init(sched_full + i, 1); mbar_init(sched_empty + i, SCHED_CONSUMERS); }
@@ -810,6 +820,10 @@ segment_kernel(const SegParams p)
         return tile;
     };
 
+    if (warp >= NDW) {
+    // every non-depthwise warp (three whole warpgroups in the two-group variant) gives registers back: one
+    // setmaxnreg site that dominates all of their code, so ptxas allocates these roles within 72 registers
+    if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == WARP_X) {
         // ======== scheduler (+ cross-layer dependency wait) + TMA producer of the activation window ========
         if (lane == 0) {
@@ -984,12 +998,12 @@ segment_kernel(const SegParams p)
                 // the slice's BN shift (shared-memory broadcast) is fetched while the TMEM load is in flight; loading it
                 // inside the loop below would chain every LDS behind the previous staging STS (possible alias) and
                 // expose its latency eight times per slice
-                float4 shv[8];
-                {
-                    const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                // (two-group variant: 72 registers for this role, so only the first half is fetched ahead)
+                constexpr int NH = ALT ? 4 : 8;
+                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                float4 shv[NH];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) shv[i] = sh4[i];
-                }
+                for (int i = 0; i < NH; ++i) shv[i] = sh4[i];
                 tmem_ld_wait();
                 if (sidx + 1 == nslice) {                      // every TMEM read of this tile has completed
                     tcgen05_fence_before();
@@ -1000,7 +1014,11 @@ segment_kernel(const SegParams p)
                 named_bar_sync(1 + half, 128);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 sh = shv[i];
+                    if (ALT && i == NH) {
+#pragma unroll
+                        for (int j = 0; j < NH; ++j) shv[j] = sh4[NH + j];
+                    }
+                    const float4 sh = shv[i % NH];
                     float4 v;
                     v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, sh.x);
                     v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, sh.y);
@@ -1023,13 +1041,18 @@ segment_kernel(const SegParams p)
             }
             PROF_ADD(1);
         }
-    } else if (warp < NDW) {
+    }
+    } else {
         // ======== depthwise producers ========
-        constexpr int R = TN / (2 * NDW);
+        if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        constexpr int R = TN / (2 * GW);
         constexpr int XP = KC / 2;
+        const int grp = ALT ? (warp >> 2) : 0;             // chunk parity this warp's group works on
+        const int wg = warp & (GW - 1);
         const int cp = lane & 15;
-        const int tw = (warp * 2 + (lane >> 4)) * R;
+        const int tw = (wg * 2 + (lane >> 4)) * R;
         int sx = 0, sb = 0; uint32_t xph = 0, bph = 0;
+        int gc = 0;                                         // running chunk index over all tiles (both groups count all)
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
             if (tile < 0) break;
@@ -1039,7 +1062,12 @@ segment_kernel(const SegParams p)
             const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res, x_w_off = L->x_w_off;
             const int len_mid = L->len_out[b];
             const bool tail_tile = t0 + TN > len_mid;      // only tiles that straddle the utterance's end need the row mask
-            for (int c = 0; c < nch; ++c) {
+            for (int c = 0; c < nch; ++c, ++gc) {
+                if (ALT && (gc & 1) != grp) {              // the other group's chunk: just keep the ring positions in step
+                    if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
+                    if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                    continue;
+                }
                 PROF_BEGIN();
                 mbar_wait(full_x + sx, xph);
                 PROF_ADD(0);
@@ -1222,6 +1250,8 @@ int tc_init()
                 VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return VASR_OK;
 }
 
@@ -1500,8 +1530,12 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     void* args[] = {(void*)&p};
-    const void* fn = split3 ? (const void*)segment_kernel<2, 4> : (const void*)segment_kernel<1, 4>;
-    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(nthreads(4)), args, smem, st));
+    // VASR_TC_ALT=1: two depthwise groups on alternate chunks (segment_kernel<., 8>)
+    static int alt = -1;
+    if (alt < 0) { const char* e = getenv("VASR_TC_ALT"); alt = (e && atoi(e) > 0) ? 1 : 0; }
+    const void* fn = alt ? (split3 ? (const void*)segment_kernel<2, 8> : (const void*)segment_kernel<1, 8>)
+                         : (split3 ? (const void*)segment_kernel<2, 4> : (const void*)segment_kernel<1, 4>);
+    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(seg_threads(alt ? 8 : 4)), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (prof_on) {
         unsigned long long h[16];
