@@ -1442,7 +1442,18 @@ bool segment_tc_layer_ok(const SubBlock& sb)
     return true;
 }
 
-static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes, int* xstages, int* bstages, int* aslots)
+// two-group variant (VASR_TC_ALT): each group holds a window stage while it computes, so it only pays off with a third
+// stage to prefetch into (measured: with 2 stages the exposed window-load latency eats the whole gain).  Ring choice
+// for it: 3 window stages, 3 operand stages, and at least two chunks of weight slots; *alt = 0 when that does not fit
+// (the 512-channel layers at K >= 51) and the one-group kernel is used instead.
+static int alt_requested()
+{
+    static int alt = -1;
+    if (alt < 0) { const char* e = getenv("VASR_TC_ALT"); alt = (e && atoi(e) > 0) ? atoi(e) : 0; }
+    return alt;
+}
+static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes, int* xstages, int* bstages, int* aslots,
+                         int* alt = nullptr)
 {
     using namespace tc;
     int mx = 0;
@@ -1452,7 +1463,18 @@ static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes
         if (sbytes > mx) mx = sbytes;
     }
     *x_stage_bytes = mx;
-    pick_rings(npart, mx, L[0].sb->cout / 256, 2 * EPI_STAGE_BYTES, xstages, bstages, aslots);
+    const int nN = L[0].sb->cout / 256;
+    pick_rings(npart, mx, nN, 2 * EPI_STAGE_BYTES, xstages, bstages, aslots);
+    if (alt) {
+        *alt = 0;
+        if (alt_requested() == 2) *alt = 1;                       // 2: force the two-group kernel with the default rings
+        else if (alt_requested() == 1) {
+            const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
+            const int overhead = 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
+            const int slots = (SMEM_LIMIT - overhead - 3 * b_stage - 3 * mx) / w_slot;
+            if (slots >= 2 * nN) { *alt = 1; *xstages = 3; *bstages = 3; *aslots = slots > 4 * nN ? 4 * nN : slots; }
+        }
+    }
 }
 
 bool segment_tc_ok(const SegLayer* L, int n, int split3)
@@ -1475,7 +1497,8 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     if (!segment_tc_ok(L, n, split3)) return set_error(VASR_EINVAL, "tcgen05 path: layers do not form a segment");
     const int npart = split3 ? 2 : 1;
     SegParams p{};
-    seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots);
+    int alt = 0;
+    seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots, &alt);
     p.nN = L[0].sb->cout / 256;
     // descriptor table (tensor maps + per-layer scalars) in device memory, cached per (layer, buffers, shape)
     LayerDesc* d_desc = nullptr;
@@ -1530,9 +1553,7 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     void* args[] = {(void*)&p};
-    // VASR_TC_ALT=1: two depthwise groups on alternate chunks (segment_kernel<., 8>)
-    static int alt = -1;
-    if (alt < 0) { const char* e = getenv("VASR_TC_ALT"); alt = (e && atoi(e) > 0) ? 1 : 0; }
+    // VASR_TC_ALT: two depthwise groups on alternate chunks (segment_kernel<., 8>) where the rings allow it
     const void* fn = alt ? (split3 ? (const void*)segment_kernel<2, 8> : (const void*)segment_kernel<1, 8>)
                          : (split3 ? (const void*)segment_kernel<2, 4> : (const void*)segment_kernel<1, 4>);
     VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(seg_threads(alt ? 8 : 4)), args, smem, st));
