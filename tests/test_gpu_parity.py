@@ -231,6 +231,27 @@ def test_host_route_equals_device_route(mode):
     assert texts == V.ids_to_text(ids_h, len_h, md["labels"])
 
 
+def test_latency_tiles_equal_throughput_tiles():
+    """Small batches run the segment kernel with 32-row tiles (latency mode), large ones with 128-row tiles: the same
+    utterances must come out bit-identical either way (same per-output FMA and accumulation order), here by running
+    two clips alone and replicated 40x inside a batch of 80."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("en15x5", "rand")
+    eng = _engine(V, md, enc_sd, dec_sd, "f16x3")
+    L = 40000
+    g = torch.Generator().manual_seed(5)
+    two = (0.1 * torch.randn(2, L, generator=g)).clamp_(-1, 1)
+    length2 = torch.tensor([L, 33333]); two[1, 33333:] = 0
+    small = eng.forward_device(two.cuda(), length2.cuda(), want_log_probs=True)
+    big = eng.forward_device(two.repeat(40, 1).cuda(), length2.repeat(40).cuda(), want_log_probs=True)
+    for key in ("enc", "log_probs", "ids"):
+        a, b = small[key], big[key]
+        assert torch.equal(a, b[:2]) and torch.equal(a, b[78:80]), key
+    ref = O.full_path(enc_sd, dec_sd, md["JasperEncoder"]["jasper"], two, length2)
+    rel = ((small["log_probs"].cpu() - ref["logp"]).norm() / ref["logp"].norm()).item()
+    assert rel < LOGIT_REL, rel
+
+
 @pytest.mark.parametrize("mode", ["f16x3"])
 def test_host_route_pipelined_sub_batches(mode):
     """Batch large enough for the encoder's two sub-batch streams and the copy/compute software pipeline of

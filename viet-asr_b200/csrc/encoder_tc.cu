@@ -748,10 +748,15 @@ static bool seg_kernel_size(int K) { return K == 11 || K == 33 || K == 39 || K =
 // warps gave back (12 warps x 24 >= 8 warps x 32); the SM's unallocated registers are not in that pool (a first
 // version that counted on them - 136 / 80 - hung in USETMAXREG.TRY_ALLOC).
 __host__ __device__ constexpr int seg_threads(int ndw) { return ndw == 8 ? 640 : nthreads(ndw); }
-template <int NPART, int NDW>
+// TR = valid time rows per tile: 128 (throughput) or 32 ("latency mode" for small batches: four times as many tiles
+// per layer, each with a quarter of the depthwise work per thread, so a lone utterance spreads over 4x the SMs and a
+// layer takes ~1/3 of the time; the MMA still computes M = 128 rows - rows >= TR of the operand are stale and their
+// accumulator rows are never stored).
+template <int NPART, int NDW, int TR>
 __global__ void __launch_bounds__(seg_threads(NDW), 1)
 segment_kernel(const SegParams p)
 {
+    static_assert(TR == TN || (TR == 32 && NDW == 4), "tile rows: 128, or 32 with one depthwise group");
     constexpr bool ALT = (NDW == 8);
     constexpr int GW = 4;                                   // depthwise warps that share a chunk
     constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = ALT ? 12 : NDW + 3;
@@ -809,7 +814,7 @@ segment_kernel(const SegParams p)
         l = item / tpl;
         const int r = item - l * tpl;
         b = p.b0 + r / p.n_tt;
-        t0 = (r % p.n_tt) * TN;
+        t0 = (r % p.n_tt) * TR;
     };
     auto next_tile = [&](int ti) -> int {
         const int slot = ti % SCHED;
@@ -864,7 +869,7 @@ segment_kernel(const SegParams p)
                             tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + s);
                         bulk_load(dst + x_w_off, dw_w + (size_t)c * tap_floats(K), (uint32_t)(tap_floats(K) * 4), full_x + s);
                     } else {
-                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(TR * KC * 4));
                         tma_load_3d(dst, &L->tm_r, (c - n_main) * KC, t0, b, full_x + s);
                     }
                     if (++s == XSTAGES) { s = 0; xph ^= 1; }
@@ -1045,7 +1050,7 @@ segment_kernel(const SegParams p)
     } else {
         // ======== depthwise producers ========
         if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-        constexpr int R = TN / (2 * GW);
+        constexpr int R = TR / (2 * GW);
         constexpr int XP = KC / 2;
         const int grp = ALT ? (warp >> 2) : 0;             // chunk parity this warp's group works on
         const int wg = warp & (GW - 1);
@@ -1061,7 +1066,7 @@ segment_kernel(const SegParams p)
             const LayerDesc* L = p.layers + l;
             const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res, x_w_off = L->x_w_off;
             const int len_mid = L->len_out[b];
-            const bool tail_tile = t0 + TN > len_mid;      // only tiles that straddle the utterance's end need the row mask
+            const bool tail_tile = t0 + TR > len_mid;      // only tiles that straddle the utterance's end need the row mask
             for (int c = 0; c < nch; ++c, ++gc) {
                 if (ALT && (gc & 1) != grp) {              // the other group's chunk: just keep the ring positions in step
                     if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
@@ -1095,8 +1100,10 @@ segment_kernel(const SegParams p)
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (p.dbg & 64) break;
-                    const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
-                    unsigned char* bh = bq[(r >> 1) & 3];
+                    // (tw is a multiple of 8 only when R >= 8; the 4-output latency tiles take the general formula)
+                    const uint32_t off = (R >= 8) ? (uint32_t)((r >> 3) * 512 + (r & 7) * 64)
+                                                  : sw64_offset(tw + r, cp >> 2) + (cp & 3) * 4;
+                    unsigned char* bh = (R >= 8) ? bq[(r >> 1) & 3] : bh0;
                     const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
                     *reinterpret_cast<__half2*>(bh + off) = h;
                     if (NPART == 2) {
@@ -1152,11 +1159,11 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, l
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 // output [B, T, C] fp32 -> 3-D map (C, T, B), box (32, 128, 1), SWIZZLE_128B (rows beyond T are clipped by the TMA)
-static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride)
+static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride, int box_rows = TN)
 {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)bstride * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)TN, 1};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 // weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 256), SWIZZLE_64B
@@ -1197,13 +1204,13 @@ static void spin_defaults(int (&spin)[4])
     for (int i = 0; i < 4; ++i) spin[i] = v[i];
 }
 
-static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_off, int* stage_bytes)
+static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_off, int* stage_bytes, int tn = TN)
 {
-    const int rows = (TN - 1) * S + (K - 1) * D + 1;
+    const int rows = (tn - 1) * S + (K - 1) * D + 1;
     int nb = (rows + 255) / 256, br = (rows + nb - 1) / nb;
     br = (br + 7) / 8 * 8;
     int bytes = nb * br * KC * 4;
-    if (bytes < TN * KC * 4) bytes = TN * KC * 4;            // residual / identity chunks load 128 rows
+    if (bytes < tn * KC * 4) bytes = tn * KC * 4;            // residual / identity chunks load one tile of rows
     *n_xbox = nb; *xbox_rows = br; *w_off = bytes;
     bytes += tap_floats(K) * 4;                               // + the chunk's depthwise taps
     *stage_bytes = (bytes + 1023) / 1024 * 1024;
@@ -1248,10 +1255,10 @@ int tc_init()
         for (int i = 0; i < 2; ++i)
             for (int j = 0; j < 2; ++j)
                 VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    const void* seg_fns[] = {(const void*)segment_kernel<2, 4, 128>, (const void*)segment_kernel<1, 4, 128>,
+                             (const void*)segment_kernel<2, 8, 128>, (const void*)segment_kernel<1, 8, 128>,
+                             (const void*)segment_kernel<2, 4, 32>, (const void*)segment_kernel<1, 4, 32>};
+    for (const void* f : seg_fns) VASR_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return VASR_OK;
 }
 
@@ -1426,7 +1433,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
 // ------------------------------------------------------------------------------------------ segment launch
 
 struct SegCacheEntry {
-    unsigned long long uid; int n; const void* x_first; const void* y_last; int B, T;
+    unsigned long long uid; int n; const void* x_first; const void* y_last; int B, T, tr;
     tc::LayerDesc* d_desc;
     int x_stage_bytes;
 };
@@ -1453,13 +1460,13 @@ static int alt_requested()
     return alt;
 }
 static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes, int* xstages, int* bstages, int* aslots,
-                         int* alt = nullptr)
+                         int* alt = nullptr, int tr = tc::TN)
 {
     using namespace tc;
     int mx = 0;
     for (int i = 0; i < n; ++i) {
         int nb, br, wo, sbytes;
-        x_geometry(L[i].sb->kernel, 1, 1, &nb, &br, &wo, &sbytes);
+        x_geometry(L[i].sb->kernel, 1, 1, &nb, &br, &wo, &sbytes, tr);
         if (sbytes > mx) mx = sbytes;
     }
     *x_stage_bytes = mx;
@@ -1467,6 +1474,7 @@ static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes
     pick_rings(npart, mx, nN, 2 * EPI_STAGE_BYTES, xstages, bstages, aslots);
     if (alt) {
         *alt = 0;
+        if (tr != TN) return;
         if (alt_requested() == 2) *alt = 1;                       // 2: force the two-group kernel with the default rings
         else if (alt_requested() == 1) {
             const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
@@ -1497,13 +1505,18 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     if (!segment_tc_ok(L, n, split3)) return set_error(VASR_EINVAL, "tcgen05 path: layers do not form a segment");
     const int npart = split3 ? 2 : 1;
     SegParams p{};
+    // latency mode: when the 128-row tiles of a layer would occupy less than half of the SMs, use 32-row tiles
+    // (VASR_TC_LAT=0 switches it off)
+    static int lat_on = -1;
+    if (lat_on < 0) { const char* e = getenv("VASR_TC_LAT"); lat_on = (e && atoi(e) == 0) ? 0 : 1; }
+    const int tr = (lat_on && ceil_div(T, TN) * nb * 2 <= g_num_sms) ? 32 : TN;
     int alt = 0;
-    seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots, &alt);
+    seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots, &alt, tr);
     p.nN = L[0].sb->cout / 256;
     // descriptor table (tensor maps + per-layer scalars) in device memory, cached per (layer, buffers, shape)
     LayerDesc* d_desc = nullptr;
     for (const SegCacheEntry& e : g_seg_cache)
-        if (e.uid == L[0].sb->uid && e.n == n && e.x_first == L[0].x && e.y_last == L[n - 1].y && e.B == B && e.T == T) { d_desc = e.d_desc; break; }
+        if (e.uid == L[0].sb->uid && e.n == n && e.x_first == L[0].x && e.y_last == L[n - 1].y && e.B == B && e.T == T && e.tr == tr) { d_desc = e.d_desc; break; }
     if (!d_desc) {
         std::vector<LayerDesc> h((size_t)n);
         int rc;
@@ -1512,13 +1525,13 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
             LayerDesc& d = h[i];
             memset(&d, 0, sizeof(d));
             int stage_bytes;
-            x_geometry(sb.kernel, 1, 1, &d.n_xbox, &d.xbox_rows, &d.x_w_off, &stage_bytes);
+            x_geometry(sb.kernel, 1, 1, &d.n_xbox, &d.xbox_rows, &d.x_w_off, &stage_bytes, tr);
             if ((rc = encode_act(&d.tm_x, L[i].x, B, T, sb.cin, L[i].xs, d.xbox_rows))) return rc;
-            if (sb.has_res) { if ((rc = encode_act(&d.tm_r, L[i].res, B, T, sb.res_cin, L[i].rs, TN))) return rc; }
+            if (sb.has_res) { if ((rc = encode_act(&d.tm_r, L[i].res, B, T, sb.res_cin, L[i].rs, tr))) return rc; }
             else d.tm_r = d.tm_x;
             memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
             memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
-            if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys))) return rc;
+            if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, tr))) return rc;
             d.dw_w = sb.dw_tc; d.shift = sb.shift; d.len_out = L[i].len_out; d.wscale_inv = sb.wscale_inv_scalar;
             d.K = sb.kernel; d.n_main = sb.cin / KC; d.n_res = sb.has_res ? sb.res_cin / KC : 0;
             d.relu = sb.relu ? 1 : 0; d.mask_tail = 1; d.pad = sb.pad;
@@ -1530,11 +1543,11 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
         }
         VASR_CUDA_OK(cudaMalloc((void**)&d_desc, sizeof(LayerDesc) * (size_t)n));
         VASR_CUDA_OK(cudaMemcpy(d_desc, h.data(), sizeof(LayerDesc) * (size_t)n, cudaMemcpyHostToDevice));
-        g_seg_cache.push_back(SegCacheEntry{L[0].sb->uid, n, L[0].x, L[n - 1].y, B, T, d_desc, p.x_stage_bytes});
+        g_seg_cache.push_back(SegCacheEntry{L[0].sb->uid, n, L[0].x, L[n - 1].y, B, T, tr, d_desc, p.x_stage_bytes});
     }
     p.layers = d_desc; p.n_layers = n;
     p.tile_counter = tile_counter; p.done = done; p.done_stride = done_stride;
-    p.T_out = T; p.b0 = b0; p.n_tt = ceil_div(T, TN); p.n_utt = nb;
+    p.T_out = T; p.b0 = b0; p.n_tt = ceil_div(T, tr); p.n_utt = nb;
     const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
                         (size_t)p.xstages * p.x_stage_bytes + 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
     const long long n_items = (long long)p.n_tt * p.n_utt * n;
@@ -1554,8 +1567,9 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     void* args[] = {(void*)&p};
     // VASR_TC_ALT: two depthwise groups on alternate chunks (segment_kernel<., 8>) where the rings allow it
-    const void* fn = alt ? (split3 ? (const void*)segment_kernel<2, 8> : (const void*)segment_kernel<1, 8>)
-                         : (split3 ? (const void*)segment_kernel<2, 4> : (const void*)segment_kernel<1, 4>);
+    const void* fn = tr != TN ? (split3 ? (const void*)segment_kernel<2, 4, 32> : (const void*)segment_kernel<1, 4, 32>)
+                     : alt    ? (split3 ? (const void*)segment_kernel<2, 8, 128> : (const void*)segment_kernel<1, 8, 128>)
+                              : (split3 ? (const void*)segment_kernel<2, 4, 128> : (const void*)segment_kernel<1, 4, 128>);
     VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(seg_threads(alt ? 8 : 4)), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (prof_on) {
