@@ -1191,12 +1191,14 @@ static const KernelEntry* find_kernel(int K, int S, int D)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // back-off of the waiting roles in ns (window producer, weight producer, MMA issuer, epilogue); VASR_TC_SPIN=a,b,c,d
-// overrides (0 = tight spin).  Defaults from the sweep in profiles/.
+// overrides.  Default 0 = plain try_wait loop: the sweep in profiles/r1_v10_spin_sweep.log shows no gain from parking
+// the waiting warps (try_wait already suspends them), and a sleeping MMA issuer or epilogue adds its wake-up latency
+// to every chunk of the latency-mode tiles.
 static void spin_defaults(int (&spin)[4])
 {
     static int v[4] = {-1, 0, 0, 0};
     if (v[0] < 0) {
-        int d[4] = {200, 50, 50, 100};
+        int d[4] = {0, 0, 0, 0};
         const char* e = getenv("VASR_TC_SPIN");
         if (e) sscanf(e, "%d,%d,%d,%d", &d[0], &d[1], &d[2], &d[3]);
         for (int i = 0; i < 4; ++i) v[i] = d[i] < 0 ? 0 : d[i];
