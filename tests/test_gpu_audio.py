@@ -2,8 +2,8 @@
 length-aware data path in front of the model (`VietASR.transcribe_signals` / `transcribe_files`).
 
 librosa / resampy are absent from the image: the resampler's parity with the packages is UNPINNED (oracle header);
-what is asserted here is CUDA kernel == scalar restatement, and that the batched pipeline gives exactly the
-transcripts of the one-utterance-at-a-time route the reference's callers use."""
+what is asserted here is CUDA kernel == scalar restatement, and that the bucketed batch pipeline gives exactly the
+transcripts of the same batches sent through `transcribe_batch` with each utterance resampled on its own."""
 import os
 import wave
 
