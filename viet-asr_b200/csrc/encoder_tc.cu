@@ -1138,6 +1138,455 @@ segment_kernel(const SegParams p)
     }
 }
 
+// =====================================================================================================================
+// CTA-pair variant of the segment kernel (VASR_TC_PAIR=1; EXPERIMENTAL: compiles, its primitives are validated by
+// tools/ubench/cta2_gemm on the B200, but the kernel itself has NOT been run yet - never selected by default).
+// A cluster of two CTAs works on two tiles of the same layer at once (tile 2u and 2u+1 of the layer's list).  Each CTA
+// does everything of the one-CTA kernel for ITS tile - window TMA, two-group depthwise, operand stores, epilogue - but
+// the 1x1 convolutions are issued by the leader as tcgen05.mma.cta_group::2 (M = 256 over both SMs): the weight block
+// of an instruction (256 output channels x 32 input channels) is split between the CTAs, so a weight slot is 16 KiB
+// instead of 32 and every SM streams half of the weights.  The 32 KiB saved pay for the third window stage that the
+// two-group depthwise needs (profiles/r1_v9_experiments.md).
+// Cross-CTA protocol (barriers live at the same offsets in both CTAs; "L:" = the leader's copy is the one in use):
+//   L:sched_full / sched_empty, tile ring   leader's scheduler claims a pair of tiles, writes the ring of both CTAs
+//   L:full_b[stage]   8 arrivals: the 4 depthwise warps of the chunk's group in EACH cta (remote arrive for rank 1)
+//   empty_b, empty_a, acc_full              released in both CTAs by tcgen05.commit ... multicast::cluster (mask 0b11)
+//   L:full_a[slot]    both CTAs' weight TMA loads (cp.async.bulk.tensor ... cta_group::2) complete on it
+//   L:acc_empty       16 arrivals: the epilogue warps of both CTAs
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v)
+{
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// wait that also acquires what OTHER CTAs of the cluster released on this barrier
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address -> same offset in the even (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar)          // arrives on `bar` in BOTH CTAs of the pair
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D = f32, A = B = f16, both K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
+constexpr uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr int W_HALF = 128 * KC * 2;            // this CTA's half of a weight block: [128 co x 64 B] fp16 = 8 KiB per part
+constexpr int PAIR_THREADS = 640;
+
+template <int NPART>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+segment_pair_kernel(const SegParams p)
+{
+    constexpr int NDW = 8, GW = 4;
+    constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10, WARP_EPI = 12;
+    // consumers of a tile-ring slot, over both CTAs: weight producer + 8 depthwise + 8 epilogue warps each, the leader's
+    // MMA warp, the peer's window producer (the leader's window producer is the scheduler itself)
+    constexpr int SCHED_CONSUMERS_PAIR = 2 * (1 + NDW + NEPI) + 2;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    unsigned char* smem = smem_raw;
+    constexpr int A_SLOT = W_HALF * NPART, B_STAGE = PART_BYTES * NPART;
+    unsigned char* a_ring = smem;
+    unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
+    unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
+    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 2 * EPI_STAGE_BYTES);
+    const int XSTAGES = p.xstages, BSTAGES = p.bstages;
+    uint64_t* full_x = bars;
+    uint64_t* empty_x = full_x + MAX_STAGES;
+    uint64_t* full_b = empty_x + MAX_STAGES;
+    uint64_t* empty_b = full_b + MAX_STAGES;
+    uint64_t* full_a = empty_b + MAX_STAGES;
+    uint64_t* empty_a = full_a + 16;
+    uint64_t* acc_full = empty_a + 16;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* sched_full = acc_empty + 2;
+    uint64_t* sched_empty = sched_full + SCHED;
+    int* tile_ring = reinterpret_cast<int*>(sched_empty + SCHED);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + SCHED);
+    float* ep_shift = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 1024);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tpl = p.n_tt * p.n_utt;                      // tiles per layer (even: checked by the host)
+    const int ppl = tpl >> 1;                              // tile pairs per layer
+    const int n_items = ppl * p.n_layers;
+    const int acc_cols = p.nN * 256;
+    const int nbuf = (acc_cols <= 256) ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, GW); }
+        for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, 2 * GW); mbar_init(empty_b + i, 1); }
+        for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * NEPI); }
+        for (int i = 0; i < SCHED; ++i) { mbar_init(sched_full + i, 1); mbar_init(sched_empty + i, SCHED_CONSUMERS_PAIR); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {                                // one warp of each CTA, same warp id in both
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                    // barriers of both CTAs are initialised before any remote arrive
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // pair item -> (layer, utterance, time tile) of THIS cta's tile
+    auto decode = [&](int item, int& l, int& b, int& t0) {
+        l = item / ppl;
+        const int r = 2 * (item - l * ppl) + (int)rank;
+        b = p.b0 + r / p.n_tt;
+        t0 = (r % p.n_tt) * TN;
+    };
+    // consumer side of the tile ring; the release goes to the leader's barrier from both CTAs
+    auto next_tile = [&](int ti) -> int {
+        const int slot = ti % SCHED;
+        mbar_wait_cluster(sched_full + slot, (ti / SCHED) & 1);
+        const int tile = tile_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(sched_empty + slot, 0));
+        return tile;
+    };
+    // window TMA producer of this CTA's tile (both CTAs); the cross-layer dependency is per utterance
+    int xs_s = 0; uint32_t xs_ph = 0;
+    auto produce_window = [&](int tile) {
+        int l, b, t0;
+        decode(tile, l, b, t0);
+        const LayerDesc* L = p.layers + l;
+        if (l > 0) {
+            const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
+            const int need = 2 * p.n_tt;
+            while (ld_acquire_gpu(flag) < need) __nanosleep(40);
+            fence_proxy_async_all();
+        }
+        const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res;
+        const int n_xbox = L->n_xbox, xbox_rows = L->xbox_rows, x_w_off = L->x_w_off, pad = L->pad;
+        const float* dw_w = L->dw_w;
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(empty_x + xs_s, xs_ph ^ 1);
+            unsigned char* dst = x_ring + (size_t)xs_s * p.x_stage_bytes;
+            if (c < n_main) {
+                mbar_arrive_expect_tx(full_x + xs_s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + tap_floats(K) * 4));
+                for (int j = 0; j < n_xbox; ++j)
+                    tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + xs_s);
+                bulk_load(dst + x_w_off, dw_w + (size_t)c * tap_floats(K), (uint32_t)(tap_floats(K) * 4), full_x + xs_s);
+            } else {
+                mbar_arrive_expect_tx(full_x + xs_s, (uint32_t)(TN * KC * 4));
+                tma_load_3d(dst, &L->tm_r, (c - n_main) * KC, t0, b, full_x + xs_s);
+            }
+            if (++xs_s == XSTAGES) { xs_s = 0; xs_ph ^= 1; }
+        }
+    };
+
+    if (warp >= NDW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == WARP_X) {
+        if (lane == 0) {
+            if (leader) {
+                // ======== scheduler of the pair + window producer of the leader's tile ========
+                for (int ti = 0;; ++ti) {
+                    const int slot = ti % SCHED;
+                    mbar_wait_cluster(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
+                    int tile = atomicAdd(p.tile_counter, 1);
+                    if (tile >= n_items) tile = -1;
+                    tile_ring[slot] = tile;
+                    st_cluster_s32(mapa_u32(tile_ring + slot, 1), tile);
+                    mbar_arrive_cluster(mapa_u32(sched_full + slot, 0));
+                    mbar_arrive_cluster(mapa_u32(sched_full + slot, 1));       // release.cluster: orders the ring store before it
+                    if (tile < 0) break;
+                    produce_window(tile);
+                }
+            } else {
+                // ======== window producer of the peer's tile ========
+                for (int ti = 0;; ++ti) {
+                    const int slot = ti % SCHED;
+                    mbar_wait_cluster(sched_full + slot, (ti / SCHED) & 1);
+                    const int tile = tile_ring[slot];
+                    mbar_arrive_cluster(mapa_u32(sched_empty + slot, 0));
+                    if (tile < 0) break;
+                    produce_window(tile);
+                }
+            }
+        }
+    } else if (warp == WARP_A) {
+        // ======== weight producer: this CTA's 128 of the 256 output channels of every block ========
+        int slot = 0; uint32_t ph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            if (lane == 0) {
+                int l, b, t0;
+                decode(tile, l, b, t0);
+                const LayerDesc* L = p.layers + l;
+                const int n_main = L->n_main, nch = L->n_main + L->n_res;
+                for (int c = 0; c < nch; ++c) {
+                    const bool res = c >= n_main;
+                    const int ci0 = (res ? c - n_main : c) * KC;
+                    for (int m = 0; m < p.nN; ++m) {
+                        mbar_wait(empty_a + slot, ph ^ 1);                    // released in both CTAs by the multicast commit
+                        // all bytes of the slot (both halves) are accounted on the leader's barrier
+                        if (leader) mbar_arrive_expect_tx(full_a + slot, (uint32_t)(2 * A_SLOT));
+                        unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
+                        const int co = m * 256 + (int)rank * 128;
+                        tma_load_2d_2sm(dst, res ? &L->tm_r_hi : &L->tm_w_hi, ci0, co, full_a + slot);
+                        if (NPART == 2) tma_load_2d_2sm(dst + W_HALF, res ? &L->tm_r_lo : &L->tm_w_lo, ci0, co, full_a + slot);
+                        if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == WARP_MMA) {
+        // ======== tcgen05.mma.cta_group::2 issuer: one thread of the leader ========
+        if (leader) {
+            int slot = 0; uint32_t ph = 0;
+            int sb = 0; uint32_t bph = 0;
+            int ab = 0; uint32_t accph = 0;
+            for (int ti = 0;; ++ti) {
+                const int tile = next_tile(ti);
+                if (tile < 0) break;
+                if (lane == 0) {
+                    int l, b, t0;
+                    decode(tile, l, b, t0);
+                    const int nch = p.layers[l].n_main + p.layers[l].n_res;
+                    mbar_wait_cluster(acc_empty + ab, accph ^ 1);            // both epilogues have drained this buffer
+                    tcgen05_fence_after();
+                    for (int c = 0; c < nch; ++c) {
+                        mbar_wait_cluster(full_b + sb, bph);                  // both CTAs' depthwise warps have published the chunk
+                        tcgen05_fence_after();
+                        const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
+                        for (int m = 0; m < p.nN; ++m) {
+                            mbar_wait(full_a + slot, ph);
+                            tcgen05_fence_after();
+                            const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
+                            const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 256);
+#pragma unroll
+                            for (int ks = 0; ks < KC / 16; ++ks) {
+                                const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
+                                const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                                umma_f16_2sm(d, x_hi, w_hi, IDESC_F16_M256_N256, (c > 0 || ks > 0) ? 1u : 0u);
+                                if (NPART == 2) {
+                                    const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
+                                    const uint64_t w_lo = make_desc_sw64(w_addr + W_HALF + ks * 32);
+                                    umma_f16_2sm(d, x_lo, w_hi, IDESC_F16_M256_N256, 1u);
+                                    umma_f16_2sm(d, x_hi, w_lo, IDESC_F16_M256_N256, 1u);
+                                }
+                            }
+                            tcgen05_commit_2sm(empty_a + slot);
+                            if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                        }
+                        tcgen05_commit_2sm(empty_b + sb);
+                        if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                    }
+                    tcgen05_commit_2sm(acc_full + ab);
+                    if (++ab == nbuf) { ab = 0; accph ^= 1; }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= WARP_EPI) {
+        // ======== epilogue of this CTA's 128 rows (as in segment_kernel; acc_empty goes to the leader) ========
+        const int q = warp & 3;
+        const int half = (warp - WARP_EPI) >> 2;
+        const int row = q * 32 + lane;
+        const bool issuer = (q == 0 && lane == 0);
+        unsigned char* stage = epi_stage + half * EPI_STAGE_BYTES;
+        const int nslice = p.nN * 4;
+        int cur_l = -1;
+        float wsc = 1.f; int relu = 0, mask_tail = 1; const int* len_out = nullptr;
+        int ab = 0; uint32_t accph = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int l, b, t0;
+            decode(tile, l, b, t0);
+            const LayerDesc* L = p.layers + l;
+            if (l != cur_l) {
+                named_bar_sync(3, NEPI * 32);
+                const float* shift = L->shift;
+                for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI * 32) ep_shift[i] = __ldg(shift + i);
+                wsc = L->wscale_inv; relu = L->relu; mask_tail = L->mask_tail; len_out = L->len_out;
+                named_bar_sync(3, NEPI * 32);
+                cur_l = l;
+            }
+            const int t = t0 + row;
+            const bool live = !(mask_tail && t >= len_out[b]);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
+            auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
+            mbar_wait(acc_full + ab, accph);
+            tcgen05_fence_after();
+            const int ab_cur = ab;
+            if (++ab == nbuf) { ab = 0; accph ^= 1; }
+            uint32_t ra[32];
+#pragma unroll 1
+            for (int sidx = 0; sidx < nslice; ++sidx) {
+                const int col0 = slice_col(sidx);
+                tmem_ld_32x32b_x32(tbase + (uint32_t)col0, ra);
+                constexpr int NH = 4;
+                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                float4 shv[NH];
+#pragma unroll
+                for (int i = 0; i < NH; ++i) shv[i] = sh4[i];
+                tmem_ld_wait();
+                if (sidx + 1 == nslice) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_u32(acc_empty + ab_cur, 0));
+                }
+                if (issuer) bulk_wait_read0();
+                named_bar_sync(1 + half, 128);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i == NH) {
+#pragma unroll
+                        for (int j = 0; j < NH; ++j) shv[j] = sh4[NH + j];
+                    }
+                    const float4 sh = shv[i % NH];
+                    float4 v;
+                    v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, sh.x);
+                    v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, sh.y);
+                    v.z = fmaf(__uint_as_float(ra[4 * i + 2]), wsc, sh.z);
+                    v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, sh.w);
+                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
+                }
+                fence_proxy_async();
+                named_bar_sync(1 + half, 128);
+                if (issuer) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
+            }
+            if (issuer) {
+                bulk_wait_all0();
+                fence_proxy_async_all();
+                __threadfence();
+                atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
+            }
+        }
+    }
+    } else {
+        // ======== depthwise producers, two groups on alternate chunks (as in segment_kernel<., 8, 128>) ========
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        constexpr int R = TN / (2 * GW);
+        constexpr int XP = KC / 2;
+        const int grp = warp >> 2;
+        const int wg = warp & (GW - 1);
+        const int cp = lane & 15;
+        const int tw = (wg * 2 + (lane >> 4)) * R;
+        int sx = 0, sb = 0; uint32_t xph = 0, bph = 0;
+        int gc = 0;
+        for (int ti = 0;; ++ti) {
+            const int tile = next_tile(ti);
+            if (tile < 0) break;
+            int l, b, t0;
+            decode(tile, l, b, t0);
+            const LayerDesc* L = p.layers + l;
+            const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res, x_w_off = L->x_w_off;
+            const int len_mid = L->len_out[b];
+            const bool tail_tile = t0 + TN > len_mid;
+            for (int c = 0; c < nch; ++c, ++gc) {
+                if ((gc & 1) != grp) {
+                    if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
+                    if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                    continue;
+                }
+                mbar_wait(full_x + sx, xph);
+                const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
+                float2 acc[R];
+                if (c < n_main) {
+                    const float2* wp = tap_base(x_ring + (size_t)sx * p.x_stage_bytes + x_w_off, cp);
+                    SEG_K_SWITCH(K, (dw_chunk_s1<KK, 1, R>(xs, wp, tw, acc)));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
+                }
+                if (tail_tile) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
+                }
+                mbar_wait(empty_b + sb, bph ^ 1);                  // multicast commit of the leader's MMA thread
+                unsigned char* bh0 = b_ring + (size_t)sb * B_STAGE;
+                unsigned char* bq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bq[q] = bh0 + (tw >> 3) * 512 + (cp & 3) * 4 + ((((uint32_t)cp >> 2) ^ (uint32_t)q) << 4);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+                    unsigned char* bh = bq[(r >> 1) & 3];
+                    const __half2 h = __floats2half2_rn(acc[r].x, acc[r].y);
+                    *reinterpret_cast<__half2*>(bh + off) = h;
+                    if (NPART == 2) {
+                        const float2 hf = __half22float2(h);
+                        *reinterpret_cast<__half2*>(bh + PART_BYTES + off) = __floats2half2_rn(acc[r].x - hf.x, acc[r].y - hf.y);
+                    }
+                }
+                // generic-proxy stores -> async proxy (the tensor core of EITHER SM reads this stage), then a
+                // cluster-scope release on the leader's barrier
+                fence_proxy_async_all();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive_cluster(mapa_u32(full_b + sb, 0)); mbar_arrive(empty_x + sx); }
+                if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
+                if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // no CTA frees TMEM or exits while its peer may still arrive on its barriers / read its smem
+    if (warp == WARP_MMA) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int encode_tm(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
                      const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle sw)
@@ -1167,11 +1616,11 @@ static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, l
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 // weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 256), SWIZZLE_64B
-static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin)
+static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin, int box_rows = 256)
 {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)Cout};
     cuuint64_t str[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, 256};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
@@ -1261,6 +1710,8 @@ int tc_init()
                              (const void*)segment_kernel<2, 8, 128>, (const void*)segment_kernel<1, 8, 128>,
                              (const void*)segment_kernel<2, 4, 32>, (const void*)segment_kernel<1, 4, 32>};
     for (const void* f : seg_fns) VASR_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return VASR_OK;
 }
 
@@ -1515,10 +1966,22 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     int alt = 0;
     seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots, &alt, tr);
     p.nN = L[0].sb->cout / 256;
+    // VASR_TC_PAIR=1 (experimental, not validated on the GPU yet): CTA-pair kernel with cta_group::2 MMAs where the
+    // layer's tile count is even and three window + three operand stages fit next to 16 KiB weight slots
+    static int pair_on = -1;
+    if (pair_on < 0) { const char* e = getenv("VASR_TC_PAIR"); pair_on = (e && atoi(e) > 0) ? 1 : 0; }
+    int pair = 0;
+    if (pair_on && tr == TN && ((ceil_div(T, TN) * nb) % 2) == 0) {
+        const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart;
+        const int overhead = 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
+        const int slots = (SMEM_LIMIT - overhead - 3 * b_stage - 3 * p.x_stage_bytes) / w_slot;
+        if (slots >= p.nN) { pair = 1; alt = 0; p.xstages = 3; p.bstages = 3; p.aslots = slots > 4 * p.nN ? 4 * p.nN : slots; }
+    }
+    const int variant = pair ? 256 : tr;                      // key of the descriptor cache (weight boxes differ)
     // descriptor table (tensor maps + per-layer scalars) in device memory, cached per (layer, buffers, shape)
     LayerDesc* d_desc = nullptr;
     for (const SegCacheEntry& e : g_seg_cache)
-        if (e.uid == L[0].sb->uid && e.n == n && e.x_first == L[0].x && e.y_last == L[n - 1].y && e.B == B && e.T == T && e.tr == tr) { d_desc = e.d_desc; break; }
+        if (e.uid == L[0].sb->uid && e.n == n && e.x_first == L[0].x && e.y_last == L[n - 1].y && e.B == B && e.T == T && e.tr == variant) { d_desc = e.d_desc; break; }
     if (!d_desc) {
         std::vector<LayerDesc> h((size_t)n);
         int rc;
@@ -1531,8 +1994,17 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
             if ((rc = encode_act(&d.tm_x, L[i].x, B, T, sb.cin, L[i].xs, d.xbox_rows))) return rc;
             if (sb.has_res) { if ((rc = encode_act(&d.tm_r, L[i].res, B, T, sb.res_cin, L[i].rs, tr))) return rc; }
             else d.tm_r = d.tm_x;
-            memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
-            memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
+            if (pair) {                                       // each CTA of a pair loads 128 of the 256 rows of a weight block
+                if ((rc = encode_w(&d.tm_w_hi, (const __half*)sb.pw_h, sb.cout, sb.cin, 128))) return rc;
+                if ((rc = encode_w(&d.tm_w_lo, (const __half*)sb.pw_l, sb.cout, sb.cin, 128))) return rc;
+                if (sb.has_res) {
+                    if ((rc = encode_w(&d.tm_r_hi, (const __half*)sb.res_h, sb.cout, sb.res_cin, 128))) return rc;
+                    if ((rc = encode_w(&d.tm_r_lo, (const __half*)sb.res_l, sb.cout, sb.res_cin, 128))) return rc;
+                } else { d.tm_r_hi = d.tm_w_hi; d.tm_r_lo = d.tm_w_lo; }
+            } else {
+                memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
+                memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
+            }
             if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, tr))) return rc;
             d.dw_w = sb.dw_tc; d.shift = sb.shift; d.len_out = L[i].len_out; d.wscale_inv = sb.wscale_inv_scalar;
             d.K = sb.kernel; d.n_main = sb.cin / KC; d.n_res = sb.has_res ? sb.res_cin / KC : 0;
@@ -1545,16 +2017,17 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
         }
         VASR_CUDA_OK(cudaMalloc((void**)&d_desc, sizeof(LayerDesc) * (size_t)n));
         VASR_CUDA_OK(cudaMemcpy(d_desc, h.data(), sizeof(LayerDesc) * (size_t)n, cudaMemcpyHostToDevice));
-        g_seg_cache.push_back(SegCacheEntry{L[0].sb->uid, n, L[0].x, L[n - 1].y, B, T, tr, d_desc, p.x_stage_bytes});
+        g_seg_cache.push_back(SegCacheEntry{L[0].sb->uid, n, L[0].x, L[n - 1].y, B, T, variant, d_desc, p.x_stage_bytes});
     }
     p.layers = d_desc; p.n_layers = n;
     p.tile_counter = tile_counter; p.done = done; p.done_stride = done_stride;
     p.T_out = T; p.b0 = b0; p.n_tt = ceil_div(T, tr); p.n_utt = nb;
-    const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
+    const size_t smem = (size_t)p.aslots * (pair ? W_HALF : W_PART) * npart + (size_t)p.bstages * PART_BYTES * npart +
                         (size_t)p.xstages * p.x_stage_bytes + 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
-    const long long n_items = (long long)p.n_tt * p.n_utt * n;
+    const long long n_items = (long long)p.n_tt * p.n_utt * n;          // tiles; the pair kernel takes two per item
     int max_ctas = g_num_sms;
     if (grid_limit > 0 && grid_limit < max_ctas) max_ctas = grid_limit;
+    if (pair) max_ctas &= ~1;
     dim3 grid((unsigned)(n_items < max_ctas ? n_items : max_ctas), 1, 1);
     static int prof_on = -1;
     static unsigned long long* d_prof = nullptr;
@@ -1569,10 +2042,11 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     void* args[] = {(void*)&p};
     // VASR_TC_ALT: two depthwise groups on alternate chunks (segment_kernel<., 8>) where the rings allow it
-    const void* fn = tr != TN ? (split3 ? (const void*)segment_kernel<2, 4, 32> : (const void*)segment_kernel<1, 4, 32>)
+    const void* fn = pair     ? (split3 ? (const void*)segment_pair_kernel<2> : (const void*)segment_pair_kernel<1>)
+                     : tr != TN ? (split3 ? (const void*)segment_kernel<2, 4, 32> : (const void*)segment_kernel<1, 4, 32>)
                      : alt    ? (split3 ? (const void*)segment_kernel<2, 8, 128> : (const void*)segment_kernel<1, 8, 128>)
                               : (split3 ? (const void*)segment_kernel<2, 4, 128> : (const void*)segment_kernel<1, 4, 128>);
-    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(seg_threads(alt ? 8 : 4)), args, smem, st));
+    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(pair ? PAIR_THREADS : seg_threads(alt ? 8 : 4)), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (prof_on) {
         unsigned long long h[16];
