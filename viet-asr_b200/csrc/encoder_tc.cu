@@ -1710,8 +1710,6 @@ int tc_init()
                              (const void*)segment_kernel<2, 8, 128>, (const void*)segment_kernel<1, 8, 128>,
                              (const void*)segment_kernel<2, 4, 32>, (const void*)segment_kernel<1, 4, 32>};
     for (const void* f : seg_fns) VASR_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return VASR_OK;
 }
 
@@ -2042,6 +2040,14 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
     void* args[] = {(void*)&p};
     // VASR_TC_ALT: two depthwise groups on alternate chunks (segment_kernel<., 8>) where the rings allow it
+    if (pair) {                                               // experimental kernel: its attributes are set on first use only
+        static bool pair_attr = false;
+        if (!pair_attr) {
+            VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+            VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+            pair_attr = true;
+        }
+    }
     const void* fn = pair     ? (split3 ? (const void*)segment_pair_kernel<2> : (const void*)segment_pair_kernel<1>)
                      : tr != TN ? (split3 ? (const void*)segment_kernel<2, 4, 32> : (const void*)segment_kernel<1, 4, 32>)
                      : alt    ? (split3 ? (const void*)segment_kernel<2, 8, 128> : (const void*)segment_kernel<1, 8, 128>)
