@@ -32,6 +32,12 @@ def _worker(rank, world, port, B, L, T, q):
         assert w.shape == (e - s, L) and ln.tolist() == [100 + i for i in range(s, e)]
         if e > s:
             assert w[0, 0].item() == s * L
+        # int16 PCM shards (audio-ingest path): same indexing, half the bytes
+        pcm = (torch.arange(B * L, dtype=torch.int32).reshape(B, L) % 30000).to(torch.int16) if rank == 0 else None
+        wp, lp = D.scatter_batch(pcm, length, B, L, dev, dtype=torch.int16)
+        assert wp.dtype == torch.int16 and wp.shape == (e - s, L) and lp.tolist() == ln.tolist()
+        if e > s:
+            assert wp[0, 1].item() == (s * L + 1) % 30000
         # "transcribe": ids = utterance index repeated, length = index
         ids = torch.stack([torch.full((T,), i, dtype=torch.int32) for i in range(s, e)]) if e > s else torch.empty((0, T), dtype=torch.int32)
         n = torch.arange(s, e, dtype=torch.int32)

@@ -29,19 +29,22 @@ def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
 
 
 def scatter_batch(wave: Optional[torch.Tensor], length: Optional[torch.Tensor], B: int, L: int,
-                  device: torch.device, src: int = 0):
-    """Rank `src` holds wave [B, L] f32 and length [B] i64; every rank returns its slice.
+                  device: torch.device, src: int = 0, dtype: torch.dtype = torch.float32):
+    """Rank `src` holds wave [B, L] (`dtype`: float32, or int16 PCM for the audio-ingest path - half the bytes on the
+    wire) and length [B] i64; every rank returns its slice.
     Uneven shards are padded to the largest shard for the collective and trimmed after."""
     world, rank = dist.get_world_size(), dist.get_rank()
     bounds = shard_bounds(B, world)
     per = max(e - s for s, e in bounds)
     my_n = bounds[rank][1] - bounds[rank][0]
-    w_out = torch.empty((per, L), dtype=torch.float32, device=device)
+    w_out = torch.empty((per, L), dtype=dtype, device=device)
     l_out = torch.empty((per,), dtype=torch.int64, device=device)
     if rank == src:
         w_list, l_list = [], []
         for s, e in bounds:
-            w = torch.zeros((per, L), dtype=torch.float32, device=device)
+            if wave.dtype != dtype:
+                raise ValueError(f"scatter_batch: wave is {wave.dtype}, dtype argument says {dtype}")
+            w = torch.zeros((per, L), dtype=dtype, device=device)
             ln = torch.full((per,), L, dtype=torch.int64, device=device)
             w[: e - s] = wave[s:e].to(device)
             ln[: e - s] = length[s:e].to(device)
