@@ -37,22 +37,25 @@ def scatter_batch(wave: Optional[torch.Tensor], length: Optional[torch.Tensor], 
     bounds = shard_bounds(B, world)
     per = max(e - s for s, e in bounds)
     my_n = bounds[rank][1] - bounds[rank][0]
+    # neither NCCL nor gloo moves int16: PCM travels as its bytes (uint8 view), any other dtype as it is
+    as_bytes = dtype == torch.int16
     w_out = torch.empty((per, L), dtype=dtype, device=device)
+    w_wire = w_out.view(torch.uint8) if as_bytes else w_out
     l_out = torch.empty((per,), dtype=torch.int64, device=device)
     if rank == src:
+        if wave.dtype != dtype:
+            raise ValueError(f"scatter_batch: wave is {wave.dtype}, dtype argument says {dtype}")
         w_list, l_list = [], []
         for s, e in bounds:
-            if wave.dtype != dtype:
-                raise ValueError(f"scatter_batch: wave is {wave.dtype}, dtype argument says {dtype}")
             w = torch.zeros((per, L), dtype=dtype, device=device)
             ln = torch.full((per,), L, dtype=torch.int64, device=device)
             w[: e - s] = wave[s:e].to(device)
             ln[: e - s] = length[s:e].to(device)
-            w_list.append(w); l_list.append(ln)
-        dist.scatter(w_out, w_list, src=src)
+            w_list.append(w.view(torch.uint8) if as_bytes else w); l_list.append(ln)
+        dist.scatter(w_wire, w_list, src=src)
         dist.scatter(l_out, l_list, src=src)
     else:
-        dist.scatter(w_out, None, src=src)
+        dist.scatter(w_wire, None, src=src)
         dist.scatter(l_out, None, src=src)
     return w_out[:my_n], l_out[:my_n]
 
