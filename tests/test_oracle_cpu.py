@@ -182,3 +182,25 @@ def test_conv_stft_restatement_equals_fft_with_periodic_window():
     a, _ = O.filterbank_features(x, torch.tensor([4000, 3000]), stft_conv=True)
     b, _ = O.filterbank_features(x, torch.tensor([4000, 3000]), stft_conv=False)
     assert a.shape == b.shape and 1e-4 < (a - b).abs().max().item() < 0.5      # periodic vs symmetric window: close, not equal
+
+
+def test_c_restatement_of_argmax_and_collapse():
+    """oracle/c/ctc_oracle.c (plain C) == the numpy/torch restatement == the reference's texts on the golden vectors,
+    plus ties (first maximal index) and the all-frames rule."""
+    from oracle import c_oracle as CO
+    for tag, kind in CASES:
+        g = load_golden(f"{tag}_{kind}")
+        logp = torch.from_numpy(g["logits"]).log_softmax(-1).numpy()
+        ids = CO.greedy_argmax(logp)
+        assert np.array_equal(ids, torch.from_numpy(logp).argmax(-1).numpy())
+        blank = logp.shape[-1] - 1
+        out, n = CO.ctc_collapse(g["ids"], blank)
+        want = O.ctc_collapse(g["ids"], blank)
+        assert [row[:k].tolist() for row, k in zip(out, n)] == want
+        assert all((row[k:] == -1).all() for row, k in zip(out, n))
+        md = model_and_weights(tag, "rand")[0]
+        assert O.ids_to_text([row[:k].tolist() for row, k in zip(out, n)], md["labels"]) == [str(t) for t in g["texts"]]
+    tie = np.zeros((1, 3, 5), np.float32); tie[0, 1, 2] = tie[0, 1, 4] = 1.0; tie[0, 2, 3] = np.nan
+    assert CO.greedy_argmax(tie).tolist() == [[0, 2, 3]] == torch.from_numpy(tie).argmax(-1).tolist()
+    out, n = CO.ctc_collapse(np.array([[3, 3, 3, 3], [0, 0, 1, 1], [0, 3, 0, 0], [3, 1, 3, 1]]), 3)
+    assert n.tolist() == [0, 2, 2, 2] and out[1, :2].tolist() == [0, 1] and out[2, :2].tolist() == [0, 0]
