@@ -67,6 +67,7 @@ def algorithmic_counts(jasper, feat_in, T_f, num_classes):
     fl_dw = fl_pw = fl_res = 0
     n_sub = 0
     wbytes = 0
+    layers = []     # (bytes, dw flops, 1x1 flops) per sub-block and utterance: for the per-layer composite floor
     for blk in jasper:
         k, s, d = blk["kernel"][0], blk["stride"][0], blk["dilation"][0]
         pad = (d * k) // 2 - 1 if d > 1 else k // 2
@@ -82,15 +83,19 @@ def algorithmic_counts(jasper, feat_in, T_f, num_classes):
             fl_pw += 2 * c * cout * T_out
             wbytes += 4 * c * cout
             n_sub += 1
+            layers.append([4 * (c * T + cout * T_out), 2 * c * k * T_out if blk.get("separable", False) else 0,
+                           2 * c * cout * T_out])
             c, T = cout, T_out
         if blk["residual"]:
             bytes_act += 4 * block_cin * block_T
             fl_res += 2 * block_cin * cout * T
             wbytes += 4 * block_cin * cout
+            layers[-1][0] += 4 * block_cin * block_T
+            layers[-1][2] += 2 * block_cin * cout * T
         cin = cout
     fl_dec = 2 * cin * num_classes * T
     return {"bytes_act": bytes_act, "flops_dw": fl_dw, "flops_pw": fl_pw, "flops_res": fl_res,
-            "flops_dec": fl_dec, "n_sub": n_sub, "weight_bytes": wbytes, "T_e": T}
+            "flops_dec": fl_dec, "n_sub": n_sub, "weight_bytes": wbytes, "T_e": T, "layers": layers}
 
 
 class ClockSampler:
@@ -444,6 +449,14 @@ def main():
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak_tf = 125.0 * 2 * 148 * sm_mhz * 1e6 / 1e12
     traffic_step = load_traffic(args.mode)
+    # composite floor: every sub-block is bound by the slowest of HBM, tensor pipe (x products per MAC) and FP32 pipe
+    # (depthwise); the sum of those per-layer maxima is the time a perfect kernel of this design would need
+    prod = 3 if args.mode == "f16x3" else 1
+    if args.mode == "fp32":
+        comp_s = sum(max(B * by / (peaks["hbm_gbs"] * 1e9), B * (dwf + pwf) / (fp32_peak_tf * 1e12)) for by, dwf, pwf in counts["layers"])
+    else:
+        comp_s = sum(max(B * by / (peaks["hbm_gbs"] * 1e9), prod * B * pwf / (peaks["bf16_tflops"] * 1e12),
+                         B * dwf / (fp32_peak_tf * 1e12)) for by, dwf, pwf in counts["layers"])
     roofline = {
         "kernel": "segment_kernel / subblock_kernel (fused depthwise + tcgen05 1x1 conv + BN + ReLU; one launch per "
                   "run of same-width sub-blocks and sub-batch)" if args.mode != "fp32"
@@ -463,6 +476,10 @@ def main():
                    "products_per_mac": 3 if args.mode == "f16x3" else 1,
                    "frac_of_issued_mma": (3 if args.mode == "f16x3" else 1) * ach_tf / peaks["bf16_tflops"],
                    "note": "peak = measured sustained bf16 cuBLAS; f16x3 issues 3 fp16 MMAs per algorithmic MAC"},
+        "composite": {"floor_ms": comp_s * 1e3, "frac": comp_s * 1e3 / enc_ms_avg,
+                      "note": "sum over the sub-blocks of max(HBM, tensor x products per MAC, FP32 depthwise) floors at the measured "
+                              "peaks / encoder-stage time: the fraction of the roofline that actually applies to each layer "
+                              "(profiles/r1_layer_table.md)"},
         "fp32_pipe": {"achieved": ach_dw_tf, "unit": "TFLOP/s (depthwise FMAs on the CUDA cores)", "peak": fp32_peak_tf,
                       "frac": ach_dw_tf / fp32_peak_tf,
                       "note": "the co-limiter SURVEY 8(d) names: the depthwise stage runs as packed FFMA2; peak = measured "
