@@ -1,20 +1,21 @@
 // Fused QuartzNet sub-block for sm_100a:   depthwise conv (CUDA cores, register sliding window)
-//   -> fp16 hi/lo split written straight into the swizzled smem B operand
+//   -> fp16 hi/lo split written straight into the swizzled smem A operand
 //   -> 1x1 conv(s) on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM)
 //   -> BN shift + residual (second GEMM chain into the same TMEM tile) + ReLU + length mask epilogue.
-// Restates one sub-block of JasperBlock.forward (nemo/collections/asr/parts/jasper.py:408-448) per launch.
+// Restates JasperBlock.forward (nemo/collections/asr/parts/jasper.py:408-448) sub-block by sub-block.
 //
 // Tile: one utterance b, TN = 128 output time steps, up to 512 output channels
 //       D[t, co] (M = 128 t, N = 256 co per MMA) = Act[t, ci] (A, K-major, written by the depthwise warps)
 //       x W[co, ci] (B, K-major, TMA), chunked over ci in KC = 32 (64-byte fp16 rows -> SWIZZLE_64B).
-//       N = 256 keeps the shared-memory operand traffic per MAC 25 % below the 128 x 128 shape and puts
-//       time on the TMEM lanes, so an epilogue thread owns one output row and stores 16-byte vectors.
+//       Time is on the TMEM lanes, so an epilogue thread owns one output row.
 // Precision: fp16 operands with a 2-term split  x = hi + lo  on both sides and three products
-//       hi*hi + lo*hi + hi*lo  (fp32-grade, mode 1) or hi*hi only (mode 2).  Weights are pre-scaled per output
-//       channel by a power of two so that hi/lo stay in fp16's normal range; the scale is undone in the epilogue.
-// Warp roles (608 threads, persistent CTA): 0..7 depthwise producers, 8 = tile scheduler + TMA producer of the
-//       activation window, 9 = TMA producer of the weight slots, 10 = tcgen05.mma issuer (+ TMEM alloc/dealloc),
-//       11..18 epilogue (two warps per TMEM lane quarter).
+//       hi*hi + lo*hi + hi*lo  (fp32-grade, mode 1) or hi*hi only (mode 2).  Weights are pre-scaled per layer
+//       by a power of two so that hi/lo stay in fp16's normal range; the scale is undone in the epilogue.
+// Three kernels share the pipeline:
+//   segment_pair_kernel  a run of stride-1 sub-blocks of one width, persistent 2-CTA clusters, cta_group::2 MMAs,
+//                        8 depthwise warps in two groups (the throughput path: 75 of the 78 sub-blocks of 15x5)
+//   segment_kernel       the same run on single CTAs with 32-row tiles (latency mode for small batches)
+//   subblock_kernel      one sub-block per launch (stride-2 first block, the dilated K = 87 layer, the final 1x1)
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cuda.h>
@@ -30,13 +31,12 @@ namespace tc {
 
 constexpr int TN = 128;                 // output time steps per CTA
 constexpr int KC = 32;                  // input channels per chunk
-// Depthwise producer warps: NDW = 8 (thread = channel pair x 8 outputs, 608 threads, <= 104 registers) or NDW = 4
-// (thread = channel pair x 16 outputs: half the shared-memory loads per FMA, 480 threads, <= 136 registers).
+constexpr int NDW = 4;                  // depthwise warps of the single-CTA kernels: thread = channel pair x 16 outputs
 constexpr int NEPI = 8;                 // epilogue warps: any 8 consecutive warps cover each TMEM lane quarter (warp & 3) twice
-__host__ __device__ constexpr int nthreads(int ndw) { return (ndw + 3 + NEPI) * 32; }
+constexpr int NTHREADS = (NDW + 3 + NEPI) * 32;            // 480: 4 depthwise, window / weight / MMA warps, 8 epilogue
 constexpr int MAX_STAGES = 4;           // upper bound of the activation-window / B-operand ring depths
 constexpr int SCHED = 4;                // depth of the tile ring
-__host__ __device__ constexpr int sched_consumers(int ndw) { return 1 /*A*/ + 1 /*MMA*/ + ndw + NEPI; }
+constexpr int SCHED_CONSUMERS = 1 /*weights*/ + 1 /*MMA*/ + NDW + NEPI;
 constexpr int PART_BYTES = 128 * KC * 2;   // activation operand: [128 t rows x 64 B] fp16 = 8 KiB per part
 constexpr int W_PART = 256 * KC * 2;       // weight operand:     [256 co rows x 64 B] fp16 = 16 KiB per part
 constexpr int MAX_CO_CTA = 512;
@@ -74,20 +74,11 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
         "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
 }
-// tight spin: only for the depthwise warps, which own the critical resource (the FP32 pipe) and wait rarely
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+    // try_wait suspends the warp in hardware for a bounded time; parking the waiting roles with nanosleep on top of
+    // it was measured to make no difference (profiles/r1_v10_spin_sweep.log)
     while (!mbar_try(bar, parity)) {}
-}
-// wait with back-off for the roles that spend most of their time waiting (producers, MMA issuer, epilogue):
-// try_wait returns after a few cycles, so a tight loop of 11 waiting warps issues ~0.6 instructions per clock per
-// scheduler (ncu: SYNCS + BRA + YIELD = 62 % of all instructions of the segment kernel) and takes issue slots away
-// from the one depthwise warp on the same scheduler.  nanosleep parks the warp instead.
-__device__ __forceinline__ void mbar_wait_bo(uint64_t* bar, uint32_t parity, uint32_t ns)
-{
-    if (mbar_try(bar, parity)) return;
-    if (ns == 0) { while (!mbar_try(bar, parity)) {} return; }
-    do { __nanosleep(ns); } while (!mbar_try(bar, parity));
 }
 __device__ __forceinline__ void fence_barrier_init()
 {
@@ -200,10 +191,9 @@ struct Params {
     int relu, mask_tail, aslots;
     int b0;                  // first utterance of this launch (sub-batch on its own stream)
     int n_tt, n_utt, n_cg;   // tiles: time tiles per utterance x utterances x output-channel groups
-    unsigned long long* prof; // optional [16] cycle counters (VASR_TC_PROF=1), see tools/
+    unsigned long long* prof; // developer builds: [32] role cycle counters (VASR_TC_PROF=1), else null
     int tma_epi;              // 1: epilogue stages 128 x 32 output slices in smem and stores them with TMA
-    int dbg;                  // timing experiments only (VASR_TC_DBG): 1 = skip MMAs, 2 = skip depthwise FMAs, 4 = skip epilogue stores
-    int spin[4];              // back-off (ns) of the waiting roles: window producer, weight producer, MMA issuer, epilogue
+    int dbg;                  // developer builds: ablation bits (VASR_TC_DBG): 1 = skip MMAs, 2 = skip depthwise FMAs, 4 = skip epilogue stores
 };
 
 // Depthwise FIR of one chunk for one thread: channel pair `xs`/`wp` (already offset by the pair), R consecutive outputs
@@ -288,21 +278,31 @@ __device__ __forceinline__ void dw_chunk_s1(const float2* __restrict__ xs, const
     }
 }
 
+// Role cycle counters and ablation switches exist in developer builds only (make dev -> libvasr_b200_dev.so,
+// -DVASR_DEV); the product library carries neither the counters nor any branch on them.
+#ifdef VASR_DEV
+#define PROF_DECL() unsigned long long pacc[4] = {0ull, 0ull, 0ull, 0ull}
 #define PROF_BEGIN() long long _pt = clock64()
 #define PROF_ADD(i) do { long long _n = clock64(); pacc[i] += (unsigned long long)(_n - _pt); _pt = _n; } while (0)
+#define DBG_ON(bit) ((p.dbg & (bit)) != 0)
+#else
+#define PROF_DECL() do {} while (0)
+#define PROF_BEGIN() do {} while (0)
+#define PROF_ADD(i) do {} while (0)
+#define DBG_ON(bit) false
+#endif
 
 // Persistent CTA (one per SM): tiles are claimed from an atomic counter by the scheduler thread and published
 // to the other roles through a small shared-memory ring; all operand rings and the TMEM accumulator buffers
 // keep running across tiles, so the epilogue of tile i overlaps the depthwise/MMA work of tile i+1.
-template <int K, int S, int D, int NPART, int NDW>
-__global__ void __launch_bounds__(nthreads(NDW), 1)
+template <int K, int S, int D, int NPART>
+__global__ void __launch_bounds__(NTHREADS, 1)
 subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_r,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const __grid_constant__ CUtensorMap tm_r_hi, const __grid_constant__ CUtensorMap tm_r_lo,
                 const __grid_constant__ CUtensorMap tm_out, const Params p)
 {
     constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = NDW + 3;
-    constexpr int SCHED_CONSUMERS = sched_consumers(NDW);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve-up: every operand tile must be 1024-byte aligned.  The dynamic window starts right after the driver's
     // 1 KiB reservation, i.e. aligned; the budget has no slack for a round-up, so fail loudly if that ever changes.
@@ -330,7 +330,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     float* ep_shift = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 1024);   // [MAX_CO_CTA] BN shift of this tile's channels
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long pacc[4] = {0ull, 0ull, 0ull, 0ull};
+    PROF_DECL();
     const int nchunks = p.n_main + p.n_res;
     const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
     const int acc_cols = p.nN * 256;                       // TMEM columns of one accumulator buffer
@@ -384,7 +384,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int gc = 0;
             for (int ti = 0;; ++ti) {
                 const int slot = ti % SCHED;
-                mbar_wait_bo(sched_empty + slot, ((ti / SCHED) & 1) ^ 1, (uint32_t)p.spin[0]);
+                mbar_wait(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
                 int tile = atomicAdd(p.tile_counter, 1);
                 if (tile >= n_tiles) tile = -1;
                 tile_ring[slot] = tile;
@@ -395,7 +395,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int s = gc % XSTAGES;
                     PROF_BEGIN();
-                    mbar_wait_bo(empty_x + s, ((gc / XSTAGES) & 1) ^ 1, (uint32_t)p.spin[0]);
+                    mbar_wait(empty_x + s, ((gc / XSTAGES) & 1) ^ 1);
                     PROF_ADD(0);
                     unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
                     if (c < p.n_main) {
@@ -426,7 +426,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const int ci0 = (res ? c - p.n_main : c) * KC;
                     for (int m = 0; m < p.nN; ++m) {
                         PROF_BEGIN();
-                        mbar_wait_bo(empty_a + slot, ph ^ 1, (uint32_t)p.spin[1]);
+                        mbar_wait(empty_a + slot, ph ^ 1);
                         PROF_ADD(0);
                         mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
@@ -448,17 +448,17 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (lane == 0) {
                 const int ab = ti % nbuf;
                 PROF_BEGIN();
-                mbar_wait_bo(acc_empty + ab, ((ti / nbuf) & 1) ^ 1, (uint32_t)p.spin[2]);     // epilogue has drained this accumulator buffer
+                mbar_wait(acc_empty + ab, ((ti / nbuf) & 1) ^ 1);     // epilogue has drained this accumulator buffer
                 PROF_ADD(2);
                 tcgen05_fence_after();
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int sb = gc % BSTAGES;
-                    mbar_wait_bo(full_b + sb, (gc / BSTAGES) & 1, (uint32_t)p.spin[2]);
+                    mbar_wait(full_b + sb, (gc / BSTAGES) & 1);
                     PROF_ADD(0);
                     tcgen05_fence_after();
                     const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
                     for (int m = 0; m < p.nN; ++m) {
-                        mbar_wait_bo(full_a + slot, ph, (uint32_t)p.spin[2]);
+                        mbar_wait(full_a + slot, ph);
                         PROF_ADD(1);
                         tcgen05_fence_after();
                         const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
@@ -468,7 +468,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                             // A operand = activations (M = 128 time rows), B operand = weights (N = 256 channels)
                             const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
                             const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
-                            if (p.dbg & 1) continue;
+                            if (DBG_ON(1)) continue;
                             umma_f16(d, x_hi, w_hi, IDESC_F16_M128_N256, (c > 0 || ks > 0) ? 1u : 0u);
                             if (NPART == 2) {
                                 const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
@@ -519,8 +519,8 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
             // +shift (BN), ReLU, length mask on one 32-channel slice held in registers, then out
             auto finish = [&](uint32_t (&rg)[32], int col0) {
-                // hoisted above the staging stores (see segment_kernel) where the register budget allows it (4 dw warps)
-                constexpr bool HOIST = (NDW == 4);
+                // hoisted above the staging stores (see segment_kernel)
+                constexpr bool HOIST = true;
                 const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
                 float4 shv[HOIST ? 8 : 1];
                 if (HOIST) {
@@ -543,17 +543,17 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.tma_epi)                             // 128-byte rows, 16-byte chunks XOR-swizzled by row (SWIZZLE_128B)
                         *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
-                    else if (row_ok && !(p.dbg & 4))
+                    else if (row_ok && !DBG_ON(4))
                         *reinterpret_cast<float4*>(orow + col0 + 4 * i) = v;
                 }
                 if (p.tma_epi) {
                     fence_proxy_async();
                     named_bar_sync(1 + half, 128);
-                    if (issuer && !(p.dbg & 4)) { tma_store_3d(&tm_out, stage, co0 + col0, t0, b); bulk_commit(); }
+                    if (issuer && !DBG_ON(4)) { tma_store_3d(&tm_out, stage, co0 + col0, t0, b); bulk_commit(); }
                 }
             };
             PROF_BEGIN();
-            mbar_wait_bo(acc_full + ab, (ti / nbuf) & 1, (uint32_t)p.spin[3]);
+            mbar_wait(acc_full + ab, (ti / nbuf) & 1);
             PROF_ADD(0);
             tcgen05_fence_after();
             // one 32-column slice in registers at a time: with 608 threads the register budget (<= 104) does not
@@ -576,13 +576,10 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         if (p.tma_epi && issuer) bulk_wait_all0();
     } else if (warp < NDW) {
         // ======== depthwise producers (warps 0..NDW-1) ========
-        // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R outputs (R = 8 with 8 warps, 16 with 4):
+        // thread = one channel PAIR (packed fp32x2 FMAs, FFMA2) x R = 16 outputs:
         //   cp = lane & 15 -> channels 2cp, 2cp+1 of the chunk;  tg = 2*warp + (lane >> 4) -> t = R*tg + r
-        // Every tap costs one window row + one tap weight from shared memory per R FFMA2, so R = 16 halves the
-        // shared-memory load traffic of the stage (the LDS return path, not the FMA pipe, is what the 8-output
-        // version waits on inside the full kernel: profiles/).
+        // Every tap costs one window row + one tap weight from shared memory per R FFMA2.
         constexpr int R = TN / (2 * NDW);
-        static_assert(R == 8 || R == 16, "depthwise warps: 4 or 8");
         constexpr int NB = (K % 3 == 0 && K > 17) ? 3 : 1;     // taps are processed in NB register-window blocks
         constexpr int KB = K / NB;
         constexpr int XP = KC / 2;                               // float2 per window row
@@ -602,7 +599,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 PROF_ADD(0);
                 const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
                 float2 acc[R];
-                if (p.dbg & 2) {
+                if (DBG_ON(2)) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) acc[r] = xs[(size_t)(tw + r) * XP];
                 } else if (c < p.n_main) {
@@ -669,6 +666,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
         }
     }
+#ifdef VASR_DEV
     if (p.prof && lane == 0) {
         // slots: dw(warp 0) 0..3 = wait full_x / compute / wait empty_b / store; X producer 4 = wait empty_x;
         // A producer 5 = wait empty_a; MMA 6..9 = wait full_b / wait full_a / wait acc_empty / issue+commit; epilogue 10..11 = wait acc_full / drain
@@ -680,6 +678,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 if (pacc[i]) atomicAdd(p.prof + base + i, pacc[i]);
         if (warp == 1) atomicAdd(p.prof + 15, 1ull);
     }
+#endif
     tcgen05_fence_before();
     __syncthreads();
     if (warp == WARP_MMA) {
@@ -718,7 +717,6 @@ struct SegParams {
     int b0, n_tt, n_utt;
     unsigned long long* prof;
     int dbg;
-    int spin[4];             // back-off (ns) of the waiting roles: window producer, weight producer, MMA issuer, epilogue
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p)
@@ -740,27 +738,18 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
     }
 static bool seg_kernel_size(int K) { return K == 11 || K == 33 || K == 39 || K == 51 || K == 63 || K == 75; }
 
-// NDW = 4: one depthwise warp per scheduler, all four on the same chunk (480 threads).
-// NDW = 8 ("two groups"): warps 0-3 and 4-7 take alternate chunks, so every scheduler holds two depthwise warps whose
-// FMA streams fill each other's stalls and fp16-split/store phases.  20 warps (one idle, so that roles fall on
-// warpgroup boundaries): the kernel starts at 96 registers per thread and re-partitions them with setmaxnreg - 128
-// for the two depthwise warpgroups, 72 for everything else.  The increase can only be served from what the CTA's own
-// warps gave back (12 warps x 24 >= 8 warps x 32); the SM's unallocated registers are not in that pool (a first
-// version that counted on them - 136 / 80 - hung in USETMAXREG.TRY_ALLOC).
-__host__ __device__ constexpr int seg_threads(int ndw) { return ndw == 8 ? 640 : nthreads(ndw); }
-// TR = valid time rows per tile: 128 (throughput) or 32 ("latency mode" for small batches: four times as many tiles
-// per layer, each with a quarter of the depthwise work per thread, so a lone utterance spreads over 4x the SMs and a
-// layer takes ~1/3 of the time; the MMA still computes M = 128 rows - rows >= TR of the operand are stale and their
-// accumulator rows are never stored).
-template <int NPART, int NDW, int TR>
-__global__ void __launch_bounds__(seg_threads(NDW), 1)
+// Single-CTA version (480 threads: one depthwise warp per scheduler, all four on the same chunk), dynamic tile
+// scheduler.  TR = valid time rows per tile: 32 = "latency mode" for small batches (four times as many tiles per layer,
+// each with a quarter of the depthwise work per thread, so a lone utterance spreads over 4x the SMs and a layer takes
+// ~1/3 of the time; the MMA still computes M = 128 rows - rows >= TR of the operand are stale and their accumulator
+// rows are never stored); 128 = the shape of the pair kernel, used where a cluster launch is not possible.
+template <int NPART, int TR>
+__global__ void __launch_bounds__(NTHREADS, 1)
 segment_kernel(const SegParams p)
 {
-    static_assert(TR == TN || (TR == 32 && NDW == 4), "tile rows: 128, or 32 with one depthwise group");
-    constexpr bool ALT = (NDW == 8);
-    constexpr int GW = 4;                                   // depthwise warps that share a chunk
-    constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = ALT ? 12 : NDW + 3;
-    constexpr int SCHED_CONSUMERS = sched_consumers(NDW);
+    static_assert(TR == TN || TR == 32, "tile rows: 128 or 32");
+    constexpr int GW = NDW;                                 // depthwise warps that share a chunk
+    constexpr int WARP_X = NDW, WARP_A = NDW + 1, WARP_MMA = NDW + 2, WARP_EPI = NDW + 3;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     unsigned char* smem = smem_raw;
@@ -786,7 +775,7 @@ segment_kernel(const SegParams p)
     float* ep_shift = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 1024);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long pacc[4] = {0ull, 0ull, 0ull, 0ull};
+    PROF_DECL();
     const int tpl = p.n_tt * p.n_utt;                      // tiles per layer
     const int n_items = tpl * p.n_layers;
     const int acc_cols = p.nN * 256;
@@ -826,16 +815,13 @@ segment_kernel(const SegParams p)
     };
 
     if (warp >= NDW) {
-    // every non-depthwise warp (three whole warpgroups in the two-group variant) gives registers back: one
-    // setmaxnreg site that dominates all of their code, so ptxas allocates these roles within 72 registers
-    if (ALT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == WARP_X) {
         // ======== scheduler (+ cross-layer dependency wait) + TMA producer of the activation window ========
         if (lane == 0) {
             int s = 0; uint32_t xph = 0;
             for (int ti = 0;; ++ti) {
                 const int slot = ti % SCHED;
-                mbar_wait_bo(sched_empty + slot, ((ti / SCHED) & 1) ^ 1, (uint32_t)p.spin[0]);
+                mbar_wait(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
                 int tile = atomicAdd(p.tile_counter, 1);
                 if (tile >= n_items) tile = -1;
                 tile_ring[slot] = tile;
@@ -858,10 +844,10 @@ segment_kernel(const SegParams p)
                 const float* dw_w = L->dw_w;
                 for (int c = 0; c < nch; ++c) {
                     PROF_BEGIN();
-                    mbar_wait_bo(empty_x + s, xph ^ 1, (uint32_t)p.spin[0]);
+                    mbar_wait(empty_x + s, xph ^ 1);
                     PROF_ADD(0);
                     unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
-                    if (p.dbg & 16) {
+                    if (DBG_ON(16)) {
                         mbar_arrive(full_x + s);
                     } else if (c < n_main) {
                         mbar_arrive_expect_tx(full_x + s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + tap_floats(K) * 4));
@@ -892,10 +878,10 @@ segment_kernel(const SegParams p)
                     const int ci0 = (res ? c - n_main : c) * KC;
                     for (int m = 0; m < p.nN; ++m) {
                         PROF_BEGIN();
-                        mbar_wait_bo(empty_a + slot, ph ^ 1, (uint32_t)p.spin[1]);
+                        mbar_wait(empty_a + slot, ph ^ 1);
                         PROF_ADD(0);
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
-                        if (p.dbg & 8) {
+                        if (DBG_ON(8)) {
                             mbar_arrive(full_a + slot);
                         } else {
                             mbar_arrive_expect_tx(full_a + slot, (uint32_t)A_SLOT);
@@ -921,16 +907,16 @@ segment_kernel(const SegParams p)
                 decode(tile, l, b, t0);
                 const int nch = p.layers[l].n_main + p.layers[l].n_res;
                 PROF_BEGIN();
-                mbar_wait_bo(acc_empty + ab, accph ^ 1, (uint32_t)p.spin[2]);
+                mbar_wait(acc_empty + ab, accph ^ 1);
                 PROF_ADD(2);
                 tcgen05_fence_after();
                 for (int c = 0; c < nch; ++c) {
-                    mbar_wait_bo(full_b + sb, bph, (uint32_t)p.spin[2]);
+                    mbar_wait(full_b + sb, bph);
                     PROF_ADD(0);
                     tcgen05_fence_after();
                     const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
                     for (int m = 0; m < p.nN; ++m) {
-                        mbar_wait_bo(full_a + slot, ph, (uint32_t)p.spin[2]);
+                        mbar_wait(full_a + slot, ph);
                         PROF_ADD(1);
                         tcgen05_fence_after();
                         const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
@@ -939,7 +925,7 @@ segment_kernel(const SegParams p)
                         for (int ks = 0; ks < KC / 16; ++ks) {
                             const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
                             const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
-                            if (p.dbg & 1) continue;
+                            if (DBG_ON(1)) continue;
                             umma_f16(d, x_hi, w_hi, IDESC_F16_M128_N256, (c > 0 || ks > 0) ? 1u : 0u);
                             if (NPART == 2) {
                                 const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
@@ -990,7 +976,7 @@ segment_kernel(const SegParams p)
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
             auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
             PROF_BEGIN();
-            mbar_wait_bo(acc_full + ab, accph, (uint32_t)p.spin[3]);
+            mbar_wait(acc_full + ab, accph);
             PROF_ADD(0);
             tcgen05_fence_after();
             const int ab_cur = ab;
@@ -1003,8 +989,7 @@ segment_kernel(const SegParams p)
                 // the slice's BN shift (shared-memory broadcast) is fetched while the TMEM load is in flight; loading it
                 // inside the loop below would chain every LDS behind the previous staging STS (possible alias) and
                 // expose its latency eight times per slice
-                // (two-group variant: 72 registers for this role, so only the first half is fetched ahead)
-                constexpr int NH = ALT ? 4 : 8;
+                constexpr int NH = 8;
                 const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
                 float4 shv[NH];
 #pragma unroll
@@ -1019,10 +1004,6 @@ segment_kernel(const SegParams p)
                 named_bar_sync(1 + half, 128);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (ALT && i == NH) {
-#pragma unroll
-                        for (int j = 0; j < NH; ++j) shv[j] = sh4[NH + j];
-                    }
                     const float4 sh = shv[i % NH];
                     float4 v;
                     v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, sh.x);
@@ -1031,11 +1012,11 @@ segment_kernel(const SegParams p)
                     v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, sh.w);
                     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!(p.dbg & 32)) *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
+                    if (!DBG_ON(32)) *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
                 }
                 fence_proxy_async();
                 named_bar_sync(1 + half, 128);
-                if (issuer && !(p.dbg & 4)) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
+                if (issuer && !DBG_ON(4)) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
             }
             if (issuer) {
                 // this half's part of the tile is in global memory: publish it to the tiles of the next layer
@@ -1049,10 +1030,8 @@ segment_kernel(const SegParams p)
     }
     } else {
         // ======== depthwise producers ========
-        if (ALT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         constexpr int R = TR / (2 * GW);
         constexpr int XP = KC / 2;
-        const int grp = ALT ? (warp >> 2) : 0;             // chunk parity this warp's group works on
         const int wg = warp & (GW - 1);
         const int cp = lane & 15;
         const int tw = (wg * 2 + (lane >> 4)) * R;
@@ -1068,11 +1047,6 @@ segment_kernel(const SegParams p)
             const int len_mid = L->len_out[b];
             const bool tail_tile = t0 + TR > len_mid;      // only tiles that straddle the utterance's end need the row mask
             for (int c = 0; c < nch; ++c, ++gc) {
-                if (ALT && (gc & 1) != grp) {              // the other group's chunk: just keep the ring positions in step
-                    if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
-                    if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
-                    continue;
-                }
                 PROF_BEGIN();
                 mbar_wait(full_x + sx, xph);
                 PROF_ADD(0);
@@ -1099,7 +1073,7 @@ segment_kernel(const SegParams p)
                 for (int q = 0; q < 4; ++q) bq[q] = bh0 + (tw >> 3) * 512 + (cp & 3) * 4 + ((((uint32_t)cp >> 2) ^ (uint32_t)q) << 4);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (p.dbg & 64) break;
+                    if (DBG_ON(64)) break;
                     // (tw is a multiple of 8 only when R >= 8; the 4-output latency tiles take the general formula)
                     const uint32_t off = (R >= 8) ? (uint32_t)((r >> 3) * 512 + (r & 7) * 64)
                                                   : sw64_offset(tw + r, cp >> 2) + (cp & 3) * 4;
@@ -1120,6 +1094,7 @@ segment_kernel(const SegParams p)
             }
         }
     }
+#ifdef VASR_DEV
     if (p.prof && lane == 0) {
         // slots as in subblock_kernel; slot 5 (xprod) additionally: cycles spent waiting for a cross-layer dependency
         int base = -1;
@@ -1130,6 +1105,7 @@ segment_kernel(const SegParams p)
                 if (pacc[i]) atomicAdd(p.prof + base + i, pacc[i]);
         if (warp == 1) atomicAdd(p.prof + 15, 1ull);
     }
+#endif
     tcgen05_fence_before();
     __syncthreads();
     if (warp == WARP_MMA) {
@@ -1139,20 +1115,32 @@ segment_kernel(const SegParams p)
 }
 
 // =====================================================================================================================
-// CTA-pair variant of the segment kernel (VASR_TC_PAIR=1; EXPERIMENTAL: compiles, its primitives are validated by
-// tools/ubench/cta2_gemm on the B200, but the kernel itself has NOT been run yet - never selected by default).
-// A cluster of two CTAs works on two tiles of the same layer at once (tile 2u and 2u+1 of the layer's list).  Each CTA
-// does everything of the one-CTA kernel for ITS tile - window TMA, two-group depthwise, operand stores, epilogue - but
-// the 1x1 convolutions are issued by the leader as tcgen05.mma.cta_group::2 (M = 256 over both SMs): the weight block
-// of an instruction (256 output channels x 32 input channels) is split between the CTAs, so a weight slot is 16 KiB
-// instead of 32 and every SM streams half of the weights.  The 32 KiB saved pay for the third window stage that the
-// two-group depthwise needs (profiles/r1_v9_experiments.md).
+// CTA-pair segment kernel (the throughput path): a cluster of two CTAs works on two tiles of the same layer at once
+// (tiles 2u and 2u+1 of the layer's list).  Each CTA does everything for ITS tile - window TMA, depthwise, operand
+// stores, epilogue - but the 1x1 convolutions are issued by the leader as tcgen05.mma.cta_group::2 (M = 256 over both
+// SMs): the weight block of an instruction (256 output channels x 32 input channels) is split between the CTAs, so a
+// weight slot is 16 KiB instead of 32, every SM streams half of the weights from L2 and the tensor core of each SM
+// reads half of the B operand.  The 32 KiB saved pay for the third window stage that the two-group depthwise needs.
+//
+// Depthwise: 8 warps in two groups (warps 0-3 / 4-7) that take alternate chunks, i.e. two depthwise warps per SM
+// sub-partition whose FMA streams fill each other's stalls and fp16-split/store phases.  The kernel starts at 96
+// registers per thread and re-partitions with setmaxnreg: 128 for the two depthwise warpgroups, 72 for the rest.
+//
+// Work list: static.  Item i = (layer, pair of tiles); cluster c executes items c, c + n_clusters, ... in increasing
+// order.  An item only depends on items with a smaller index (previous layer, same utterance), and every cluster works
+// through its list in order, so the smallest unfinished item can always run: no deadlock as long as the kernel's
+// clusters become resident eventually (grid <= SM count).  A layer with an odd number of tiles pairs its last tile
+// with a duplicate of itself: the peer computes it too but neither stores nor publishes it.
+//
 // Cross-CTA protocol (barriers live at the same offsets in both CTAs; "L:" = the leader's copy is the one in use):
-//   L:sched_full / sched_empty, tile ring   leader's scheduler claims a pair of tiles, writes the ring of both CTAs
 //   L:full_b[stage]   8 arrivals: the 4 depthwise warps of the chunk's group in EACH cta (remote arrive for rank 1)
 //   empty_b, empty_a, acc_full              released in both CTAs by tcgen05.commit ... multicast::cluster (mask 0b11)
 //   L:full_a[slot]    both CTAs' weight TMA loads (cp.async.bulk.tensor ... cta_group::2) complete on it
 //   L:acc_empty       16 arrivals: the epilogue warps of both CTAs
+// Remote arrives use the default (release.cta) semantics like CUTLASS's ClusterBarrier::arrive: what they publish is
+// either consumed by the arriving CTA's own tensor core (operand stage: generic-proxy stores + fence.proxy.async in
+// the writing CTA) or is no data at all (accumulator drained).  A cluster-scope release costs a MEMBAR.ALL.GPU per
+// arrive (measured: +1600 cycles per chunk in the depthwise store phase).
 // =====================================================================================================================
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -1171,27 +1159,9 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v)
-{
-    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-// wait that also acquires what OTHER CTAs of the cluster released on this barrier
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address -> same offset in the even (leader) CTA
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar)
@@ -1214,20 +1184,30 @@ __device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar)          // ar
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 // D = f32, A = B = f16, both K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
 constexpr uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr int W_HALF = 128 * KC * 2;            // this CTA's half of a weight block: [128 co x 64 B] fp16 = 8 KiB per part
 constexpr int PAIR_THREADS = 640;
+constexpr int EPI_SUB_COLS = 16;                // output channels per epilogue sub-slice (64-byte rows, SWIZZLE_64B)
+constexpr int EPI_SUB_BYTES = TN * EPI_SUB_COLS * 4;          // 8 KiB; two per epilogue half-group = 32 KiB in all
 
 template <int NPART>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 segment_pair_kernel(const SegParams p)
 {
-    constexpr int NDW = 8, GW = 4;
+    constexpr int NDW_PAIR = 8, GW = 4;                    // depthwise warps (two groups of GW)
     constexpr int WARP_X = 8, WARP_A = 9, WARP_MMA = 10, WARP_EPI = 12;
-    // consumers of a tile-ring slot, over both CTAs: weight producer + 8 depthwise + 8 epilogue warps each, the leader's
-    // MMA warp, the peer's window producer (the leader's window producer is the scheduler itself)
-    constexpr int SCHED_CONSUMERS_PAIR = 2 * (1 + NDW + NEPI) + 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     unsigned char* smem = smem_raw;
@@ -1235,8 +1215,8 @@ segment_pair_kernel(const SegParams p)
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
     unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
-    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 2 * EPI_STAGE_BYTES);
+    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;      // [2 halves][2][128 rows x 64 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 4 * EPI_SUB_BYTES);
     const int XSTAGES = p.xstages, BSTAGES = p.bstages;
     uint64_t* full_x = bars;
     uint64_t* empty_x = full_x + MAX_STAGES;
@@ -1246,18 +1226,17 @@ segment_pair_kernel(const SegParams p)
     uint64_t* empty_a = full_a + 16;
     uint64_t* acc_full = empty_a + 16;
     uint64_t* acc_empty = acc_full + 2;
-    uint64_t* sched_full = acc_empty + 2;
-    uint64_t* sched_empty = sched_full + SCHED;
-    int* tile_ring = reinterpret_cast<int*>(sched_empty + SCHED);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_ring + SCHED);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* ep_shift = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 1024);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    PROF_DECL();
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int tpl = p.n_tt * p.n_utt;                      // tiles per layer (even: checked by the host)
-    const int ppl = tpl >> 1;                              // tile pairs per layer
+    const int tpl = p.n_tt * p.n_utt;                      // tiles per layer
+    const int ppl = (tpl + 1) >> 1;                        // tile pairs per layer (the last one may hold a duplicate)
     const int n_items = ppl * p.n_layers;
+    const int item0 = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
     const int acc_cols = p.nN * 256;
     const int nbuf = (acc_cols <= 256) ? 2 : 1;
 
@@ -1266,7 +1245,6 @@ segment_pair_kernel(const SegParams p)
         for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, 2 * GW); mbar_init(empty_b + i, 1); }
         for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * NEPI); }
-        for (int i = 0; i < SCHED; ++i) { mbar_init(sched_full + i, 1); mbar_init(sched_empty + i, SCHED_CONSUMERS_PAIR); }
         fence_barrier_init();
     }
     if (warp == WARP_MMA) {                                // one warp of each CTA, same warp id in both
@@ -1279,99 +1257,70 @@ segment_pair_kernel(const SegParams p)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // pair item -> (layer, utterance, time tile) of THIS cta's tile
-    auto decode = [&](int item, int& l, int& b, int& t0) {
+    // item -> (layer, utterance, time tile) of THIS cta's tile; dup = the layer's odd last tile, computed by both CTAs
+    auto decode = [&](int item, int& l, int& b, int& t0, bool& dup) {
         l = item / ppl;
-        const int r = 2 * (item - l * ppl) + (int)rank;
+        int r = 2 * (item - l * ppl) + (int)rank;
+        dup = r >= tpl;
+        if (dup) r = tpl - 1;
         b = p.b0 + r / p.n_tt;
         t0 = (r % p.n_tt) * TN;
     };
-    // consumer side of the tile ring; the release goes to the leader's barrier from both CTAs
-    auto next_tile = [&](int ti) -> int {
-        const int slot = ti % SCHED;
-        mbar_wait_cluster(sched_full + slot, (ti / SCHED) & 1);
-        const int tile = tile_ring[slot];
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_u32(sched_empty + slot, 0));
-        return tile;
-    };
-    // window TMA producer of this CTA's tile (both CTAs); the cross-layer dependency is per utterance
-    int xs_s = 0; uint32_t xs_ph = 0;
-    auto produce_window = [&](int tile) {
-        int l, b, t0;
-        decode(tile, l, b, t0);
-        const LayerDesc* L = p.layers + l;
-        if (l > 0) {
-            const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
-            const int need = 2 * p.n_tt;
-            while (ld_acquire_gpu(flag) < need) __nanosleep(40);
-            fence_proxy_async_all();
-        }
-        const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res;
-        const int n_xbox = L->n_xbox, xbox_rows = L->xbox_rows, x_w_off = L->x_w_off, pad = L->pad;
-        const float* dw_w = L->dw_w;
-        for (int c = 0; c < nch; ++c) {
-            mbar_wait(empty_x + xs_s, xs_ph ^ 1);
-            unsigned char* dst = x_ring + (size_t)xs_s * p.x_stage_bytes;
-            if (c < n_main) {
-                mbar_arrive_expect_tx(full_x + xs_s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + tap_floats(K) * 4));
-                for (int j = 0; j < n_xbox; ++j)
-                    tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + xs_s);
-                bulk_load(dst + x_w_off, dw_w + (size_t)c * tap_floats(K), (uint32_t)(tap_floats(K) * 4), full_x + xs_s);
-            } else {
-                mbar_arrive_expect_tx(full_x + xs_s, (uint32_t)(TN * KC * 4));
-                tma_load_3d(dst, &L->tm_r, (c - n_main) * KC, t0, b, full_x + xs_s);
-            }
-            if (++xs_s == XSTAGES) { xs_s = 0; xs_ph ^= 1; }
-        }
-    };
 
-    if (warp >= NDW) {
+    if (warp >= NDW_PAIR) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == WARP_X) {
+        // ======== TMA producer of this CTA's activation windows (+ cross-layer dependency wait) ========
         if (lane == 0) {
-            if (leader) {
-                // ======== scheduler of the pair + window producer of the leader's tile ========
-                for (int ti = 0;; ++ti) {
-                    const int slot = ti % SCHED;
-                    mbar_wait_cluster(sched_empty + slot, ((ti / SCHED) & 1) ^ 1);
-                    int tile = atomicAdd(p.tile_counter, 1);
-                    if (tile >= n_items) tile = -1;
-                    tile_ring[slot] = tile;
-                    st_cluster_s32(mapa_u32(tile_ring + slot, 1), tile);
-                    mbar_arrive_cluster(mapa_u32(sched_full + slot, 0));
-                    mbar_arrive_cluster(mapa_u32(sched_full + slot, 1));       // release.cluster: orders the ring store before it
-                    if (tile < 0) break;
-                    produce_window(tile);
+            int s = 0; uint32_t xph = 0;
+            for (int item = item0; item < n_items; item += item_step) {
+                int l, b, t0; bool dup;
+                decode(item, l, b, t0, dup);
+                const LayerDesc* L = p.layers + l;
+                if (l > 0) {
+                    // every tile of layer l-1 of this utterance has been stored (both epilogue halves of each time tile)
+                    const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
+                    const int need = 2 * p.n_tt;
+                    PROF_BEGIN();
+                    while (ld_acquire_gpu(flag) < need) __nanosleep(40);
+                    PROF_ADD(1);
+                    fence_proxy_async_all();        // the TMA (async proxy) reads below are ordered after the acquire
                 }
-            } else {
-                // ======== window producer of the peer's tile ========
-                for (int ti = 0;; ++ti) {
-                    const int slot = ti % SCHED;
-                    mbar_wait_cluster(sched_full + slot, (ti / SCHED) & 1);
-                    const int tile = tile_ring[slot];
-                    mbar_arrive_cluster(mapa_u32(sched_empty + slot, 0));
-                    if (tile < 0) break;
-                    produce_window(tile);
+                const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res;
+                const int n_xbox = L->n_xbox, xbox_rows = L->xbox_rows, x_w_off = L->x_w_off, pad = L->pad;
+                const float* dw_w = L->dw_w;
+                for (int c = 0; c < nch; ++c) {
+                    PROF_BEGIN();
+                    mbar_wait(empty_x + s, xph ^ 1);
+                    PROF_ADD(0);
+                    unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
+                    if (c < n_main) {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + tap_floats(K) * 4));
+                        for (int j = 0; j < n_xbox; ++j)
+                            tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + s);
+                        bulk_load(dst + x_w_off, dw_w + (size_t)c * tap_floats(K), (uint32_t)(tap_floats(K) * 4), full_x + s);
+                    } else {
+                        mbar_arrive_expect_tx(full_x + s, (uint32_t)(TN * KC * 4));
+                        tma_load_3d(dst, &L->tm_r, (c - n_main) * KC, t0, b, full_x + s);
+                    }
+                    if (++s == XSTAGES) { s = 0; xph ^= 1; }
                 }
             }
         }
     } else if (warp == WARP_A) {
         // ======== weight producer: this CTA's 128 of the 256 output channels of every block ========
-        int slot = 0; uint32_t ph = 0;
-        for (int ti = 0;; ++ti) {
-            const int tile = next_tile(ti);
-            if (tile < 0) break;
-            if (lane == 0) {
-                int l, b, t0;
-                decode(tile, l, b, t0);
-                const LayerDesc* L = p.layers + l;
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (int item = item0; item < n_items; item += item_step) {
+                const LayerDesc* L = p.layers + item / ppl;
                 const int n_main = L->n_main, nch = L->n_main + L->n_res;
                 for (int c = 0; c < nch; ++c) {
                     const bool res = c >= n_main;
                     const int ci0 = (res ? c - n_main : c) * KC;
                     for (int m = 0; m < p.nN; ++m) {
+                        PROF_BEGIN();
                         mbar_wait(empty_a + slot, ph ^ 1);                    // released in both CTAs by the multicast commit
+                        PROF_ADD(0);
                         // all bytes of the slot (both halves) are accounted on the leader's barrier
                         if (leader) mbar_arrive_expect_tx(full_a + slot, (uint32_t)(2 * A_SLOT));
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
@@ -1382,137 +1331,136 @@ segment_pair_kernel(const SegParams p)
                     }
                 }
             }
-            __syncwarp();
         }
     } else if (warp == WARP_MMA) {
         // ======== tcgen05.mma.cta_group::2 issuer: one thread of the leader ========
-        if (leader) {
+        if (leader && lane == 0) {
             int slot = 0; uint32_t ph = 0;
             int sb = 0; uint32_t bph = 0;
             int ab = 0; uint32_t accph = 0;
-            for (int ti = 0;; ++ti) {
-                const int tile = next_tile(ti);
-                if (tile < 0) break;
-                if (lane == 0) {
-                    int l, b, t0;
-                    decode(tile, l, b, t0);
-                    const int nch = p.layers[l].n_main + p.layers[l].n_res;
-                    mbar_wait_cluster(acc_empty + ab, accph ^ 1);            // both epilogues have drained this buffer
+            for (int item = item0; item < n_items; item += item_step) {
+                const LayerDesc* L = p.layers + item / ppl;
+                const int nch = L->n_main + L->n_res;
+                PROF_BEGIN();
+                mbar_wait(acc_empty + ab, accph ^ 1);            // both epilogues have drained this buffer
+                PROF_ADD(2);
+                tcgen05_fence_after();
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(full_b + sb, bph);                  // both CTAs' depthwise warps have published the chunk
+                    PROF_ADD(0);
                     tcgen05_fence_after();
-                    for (int c = 0; c < nch; ++c) {
-                        mbar_wait_cluster(full_b + sb, bph);                  // both CTAs' depthwise warps have published the chunk
+                    const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
+                    for (int m = 0; m < p.nN; ++m) {
+                        mbar_wait(full_a + slot, ph);
+                        PROF_ADD(1);
                         tcgen05_fence_after();
-                        const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * B_STAGE);
-                        for (int m = 0; m < p.nN; ++m) {
-                            mbar_wait(full_a + slot, ph);
-                            tcgen05_fence_after();
-                            const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
-                            const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 256);
+                        const uint32_t w_addr = smem_u32(a_ring + (size_t)slot * A_SLOT);
+                        const uint32_t d = tmem_base + (uint32_t)(ab * acc_cols + m * 256);
 #pragma unroll
-                            for (int ks = 0; ks < KC / 16; ++ks) {
-                                const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
-                                const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
-                                umma_f16_2sm(d, x_hi, w_hi, IDESC_F16_M256_N256, (c > 0 || ks > 0) ? 1u : 0u);
-                                if (NPART == 2) {
-                                    const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
-                                    const uint64_t w_lo = make_desc_sw64(w_addr + W_HALF + ks * 32);
-                                    umma_f16_2sm(d, x_lo, w_hi, IDESC_F16_M256_N256, 1u);
-                                    umma_f16_2sm(d, x_hi, w_lo, IDESC_F16_M256_N256, 1u);
-                                }
+                        for (int ks = 0; ks < KC / 16; ++ks) {
+                            const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
+                            const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                            umma_f16_2sm(d, x_hi, w_hi, IDESC_F16_M256_N256, (c > 0 || ks > 0) ? 1u : 0u);
+                            if (NPART == 2) {
+                                const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
+                                const uint64_t w_lo = make_desc_sw64(w_addr + W_HALF + ks * 32);
+                                umma_f16_2sm(d, x_lo, w_hi, IDESC_F16_M256_N256, 1u);
+                                umma_f16_2sm(d, x_hi, w_lo, IDESC_F16_M256_N256, 1u);
                             }
-                            tcgen05_commit_2sm(empty_a + slot);
-                            if (++slot == p.aslots) { slot = 0; ph ^= 1; }
                         }
-                        tcgen05_commit_2sm(empty_b + sb);
-                        if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                        tcgen05_commit_2sm(empty_a + slot);
+                        PROF_ADD(3);
+                        if (++slot == p.aslots) { slot = 0; ph ^= 1; }
                     }
-                    tcgen05_commit_2sm(acc_full + ab);
-                    if (++ab == nbuf) { ab = 0; accph ^= 1; }
+                    tcgen05_commit_2sm(empty_b + sb);
+                    if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
                 }
-                __syncwarp();
+                tcgen05_commit_2sm(acc_full + ab);
+                if (++ab == nbuf) { ab = 0; accph ^= 1; }
             }
         }
     } else if (warp >= WARP_EPI) {
-        // ======== epilogue of this CTA's 128 rows (as in segment_kernel; acc_empty goes to the leader) ========
+        // ======== epilogue of this CTA's 128 rows: TMEM -> +shift, ReLU, mask -> smem staging -> TMA store ========
+        // 16-column sub-slices through two 8 KiB staging buffers per half-group: the TMA store of sub-slice i reads its
+        // buffer while sub-slice i+1 is loaded from TMEM and written into the other one.
         const int q = warp & 3;
         const int half = (warp - WARP_EPI) >> 2;
         const int row = q * 32 + lane;
         const bool issuer = (q == 0 && lane == 0);
-        unsigned char* stage = epi_stage + half * EPI_STAGE_BYTES;
-        const int nslice = p.nN * 4;
+        unsigned char* stage = epi_stage + half * 2 * EPI_SUB_BYTES;
+        const uint32_t acc_empty_leader = mapa_u32(acc_empty, 0);
+        const int nsub = p.nN * (128 / EPI_SUB_COLS);
+        const uint32_t row_off = (uint32_t)row * 64u, row_sw = ((uint32_t)row >> 1) & 3u;
         int cur_l = -1;
-        float wsc = 1.f; int relu = 0, mask_tail = 1; const int* len_out = nullptr;
+        float wsc = 1.f; int relu = 0; const int* len_out = nullptr;
         int ab = 0; uint32_t accph = 0;
-        for (int ti = 0;; ++ti) {
-            const int tile = next_tile(ti);
-            if (tile < 0) break;
-            int l, b, t0;
-            decode(tile, l, b, t0);
+        for (int item = item0; item < n_items; item += item_step) {
+            int l, b, t0; bool dup;
+            decode(item, l, b, t0, dup);
             const LayerDesc* L = p.layers + l;
-            if (l != cur_l) {
+            if (l != cur_l) {                                  // per-channel BN shift + scalars of the new layer
                 named_bar_sync(3, NEPI * 32);
                 const float* shift = L->shift;
                 for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI * 32) ep_shift[i] = __ldg(shift + i);
-                wsc = L->wscale_inv; relu = L->relu; mask_tail = L->mask_tail; len_out = L->len_out;
+                wsc = L->wscale_inv; relu = L->relu; len_out = L->len_out;
                 named_bar_sync(3, NEPI * 32);
                 cur_l = l;
             }
-            const int t = t0 + row;
-            const bool live = !(mask_tail && t >= len_out[b]);
+            const bool live = (t0 + row) < len_out[b];          // rows t >= len are stored as zeros (every segment layer masks its tail)
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
-            auto slice_col = [&](int sidx) { return (sidx >> 2) * 256 + (half * 4 + (sidx & 3)) * 32; };
+            PROF_BEGIN();
             mbar_wait(acc_full + ab, accph);
+            PROF_ADD(0);
             tcgen05_fence_after();
             const int ab_cur = ab;
             if (++ab == nbuf) { ab = 0; accph ^= 1; }
-            uint32_t ra[32];
+            uint32_t ra[16];
 #pragma unroll 1
-            for (int sidx = 0; sidx < nslice; ++sidx) {
-                const int col0 = slice_col(sidx);
-                tmem_ld_32x32b_x32(tbase + (uint32_t)col0, ra);
-                constexpr int NH = 4;
+            for (int s = 0; s < nsub; ++s) {
+                const int col0 = (s >> 3) * 256 + half * 128 + (s & 7) * EPI_SUB_COLS;
+                tmem_ld_32x32b_x16(tbase + (uint32_t)col0, ra);
+                // the sub-slice's BN shift (shared-memory broadcast) is fetched while the TMEM load is in flight
                 const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
-                float4 shv[NH];
+                float4 shv[4];
 #pragma unroll
-                for (int i = 0; i < NH; ++i) shv[i] = sh4[i];
+                for (int i = 0; i < 4; ++i) shv[i] = sh4[i];
                 tmem_ld_wait();
-                if (sidx + 1 == nslice) {
+                if (s + 1 == nsub) {                           // every TMEM read of this tile has completed
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_u32(acc_empty + ab_cur, 0));
+                    if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * (uint32_t)ab_cur);
                 }
-                if (issuer) bulk_wait_read0();
+                unsigned char* buf = stage + (s & 1) * EPI_SUB_BYTES;
+                if (issuer) bulk_wait_read1();                 // the store issued two sub-slices ago has left this buffer
                 named_bar_sync(1 + half, 128);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i == NH) {
-#pragma unroll
-                        for (int j = 0; j < NH; ++j) shv[j] = sh4[NH + j];
-                    }
-                    const float4 sh = shv[i % NH];
+                for (int i = 0; i < 4; ++i) {
                     float4 v;
-                    v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, sh.x);
-                    v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, sh.y);
-                    v.z = fmaf(__uint_as_float(ra[4 * i + 2]), wsc, sh.z);
-                    v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, sh.w);
+                    v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, shv[i].x);
+                    v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, shv[i].y);
+                    v.z = fmaf(__uint_as_float(ra[4 * i + 2]), wsc, shv[i].z);
+                    v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, shv[i].w);
                     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(stage + row * 128 + ((i ^ (row & 7)) << 4)) = v;
+                    *reinterpret_cast<float4*>(buf + row_off + (((uint32_t)i ^ row_sw) << 4)) = v;   // SWIZZLE_64B
                 }
                 fence_proxy_async();
                 named_bar_sync(1 + half, 128);
-                if (issuer) { tma_store_3d(&L->tm_out, stage, col0, t0, b); bulk_commit(); }
+                if (issuer && !dup) { tma_store_3d(&L->tm_out, buf, col0, t0, b); bulk_commit(); }
             }
-            if (issuer) {
+            if (issuer && !dup) {
+                // this half's part of the tile is in global memory: publish it to the tiles of the next layer
                 bulk_wait_all0();
                 fence_proxy_async_all();
                 __threadfence();
                 atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
             }
+            PROF_ADD(1);
         }
+        if (issuer) bulk_wait_all0();
     }
     } else {
-        // ======== depthwise producers, two groups on alternate chunks (as in segment_kernel<., 8, 128>) ========
+        // ======== depthwise producers, two groups on alternate chunks ========
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         constexpr int R = TN / (2 * GW);
         constexpr int XP = KC / 2;
@@ -1520,24 +1468,25 @@ segment_pair_kernel(const SegParams p)
         const int wg = warp & (GW - 1);
         const int cp = lane & 15;
         const int tw = (wg * 2 + (lane >> 4)) * R;
+        const uint32_t full_b_leader = mapa_u32(full_b, 0);
         int sx = 0, sb = 0; uint32_t xph = 0, bph = 0;
-        int gc = 0;
-        for (int ti = 0;; ++ti) {
-            const int tile = next_tile(ti);
-            if (tile < 0) break;
-            int l, b, t0;
-            decode(tile, l, b, t0);
+        int gc = 0;                                         // running chunk index over all tiles (both groups count all)
+        for (int item = item0; item < n_items; item += item_step) {
+            int l, b, t0; bool dup;
+            decode(item, l, b, t0, dup);
             const LayerDesc* L = p.layers + l;
             const int K = L->K, n_main = L->n_main, nch = L->n_main + L->n_res, x_w_off = L->x_w_off;
             const int len_mid = L->len_out[b];
-            const bool tail_tile = t0 + TN > len_mid;
+            const bool tail_tile = t0 + TN > len_mid;      // only tiles that straddle the utterance's end need the row mask
             for (int c = 0; c < nch; ++c, ++gc) {
-                if ((gc & 1) != grp) {
+                if ((gc & 1) != grp) {                     // the other group's chunk: just keep the ring positions in step
                     if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
                     if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
                     continue;
                 }
+                PROF_BEGIN();
                 mbar_wait(full_x + sx, xph);
+                PROF_ADD(0);
                 const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
                 float2 acc[R];
                 if (c < n_main) {
@@ -1552,7 +1501,9 @@ segment_pair_kernel(const SegParams p)
                     for (int r = 0; r < R; ++r)
                         if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
                 }
+                PROF_ADD(1);
                 mbar_wait(empty_b + sb, bph ^ 1);                  // multicast commit of the leader's MMA thread
+                PROF_ADD(2);
                 unsigned char* bh0 = b_ring + (size_t)sb * B_STAGE;
                 unsigned char* bq[4];
 #pragma unroll
@@ -1568,16 +1519,37 @@ segment_pair_kernel(const SegParams p)
                         *reinterpret_cast<__half2*>(bh + PART_BYTES + off) = __floats2half2_rn(acc[r].x - hf.x, acc[r].y - hf.y);
                     }
                 }
-                // generic-proxy stores -> async proxy (the tensor core of EITHER SM reads this stage), then a
-                // cluster-scope release on the leader's barrier
-                fence_proxy_async_all();
+                // generic-proxy stores -> async proxy (this SM's tensor core reads this stage), then the arrive on the
+                // leader's barrier
+                fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive_cluster(mapa_u32(full_b + sb, 0)); mbar_arrive(empty_x + sx); }
+                if (lane == 0) {
+                    if (leader) mbar_arrive(full_b + sb); else mbar_arrive_remote(full_b_leader + 8u * (uint32_t)sb);
+                    mbar_arrive(empty_x + sx);
+                }
                 if (++sx == XSTAGES) { sx = 0; xph ^= 1; }
                 if (++sb == BSTAGES) { sb = 0; bph ^= 1; }
+                PROF_ADD(3);
             }
         }
     }
+#ifdef VASR_DEV
+    if (p.prof && lane == 0) {
+        // leader CTA: dw group 0 (warp 0) 0..3, window producer 4..5, weight producer 12, MMA 6..9, epilogue 10..11;
+        // peer CTA: dw group 1 (warp 4) -> 16..19, epilogue -> 20..21, window producer 22..23
+        int base = -1;
+        if (leader) {
+            if (warp == 0) base = 0; else if (warp == WARP_X) base = 4; else if (warp == WARP_A) base = 12;
+            else if (warp == WARP_MMA) base = 6; else if (warp == WARP_EPI) base = 10;
+        } else {
+            if (warp == 4) base = 16; else if (warp == WARP_EPI) base = 20; else if (warp == WARP_X) base = 22;
+        }
+        if (base >= 0)
+            for (int i = 0; i < 4; ++i)
+                if (pacc[i]) atomicAdd(p.prof + base + i, pacc[i]);
+        if (warp == 1 && leader) atomicAdd(p.prof + 15, 1ull);
+    }
+#endif
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();            // no CTA frees TMEM or exits while its peer may still arrive on its barriers / read its smem
@@ -1607,13 +1579,16 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, l
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
-// output [B, T, C] fp32 -> 3-D map (C, T, B), box (32, 128, 1), SWIZZLE_128B (rows beyond T are clipped by the TMA)
-static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride, int box_rows = TN)
+// output [B, T, C] fp32 -> 3-D map (C, T, B), box (cols, rows, 1); 32 columns: SWIZZLE_128B, 16 columns: SWIZZLE_64B
+// (rows beyond T are clipped by the TMA)
+static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride, int box_rows = TN,
+                      int box_cols = 32)
 {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)bstride * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
-    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box,
+                     box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 // weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 256), SWIZZLE_64B
 static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin, int box_rows = 256)
@@ -1624,9 +1599,8 @@ static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin, int 
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-struct KernelEntry { int K, S, D; const void* fn[2][2]; };   // [f16x3 ? 0 : 1][8 dw warps ? 0 : 1 (4 dw warps)]
-#define TC_ENTRY(k, s, d) {k, s, d, {{(const void*)subblock_kernel<k, s, d, 2, 8>, (const void*)subblock_kernel<k, s, d, 2, 4>}, \
-                                     {(const void*)subblock_kernel<k, s, d, 1, 8>, (const void*)subblock_kernel<k, s, d, 1, 4>}}}
+struct KernelEntry { int K, S, D; const void* fn[2]; };   // [0] f16x3 (hi + lo parts), [1] f16x1
+#define TC_ENTRY(k, s, d) {k, s, d, {(const void*)subblock_kernel<k, s, d, 2>, (const void*)subblock_kernel<k, s, d, 1>}}
 static const KernelEntry g_kernels[] = {
     TC_ENTRY(1, 1, 1), TC_ENTRY(33, 2, 1), TC_ENTRY(33, 1, 1), TC_ENTRY(39, 1, 1), TC_ENTRY(51, 1, 1),
     TC_ENTRY(63, 1, 1), TC_ENTRY(75, 1, 1), TC_ENTRY(87, 1, 2), TC_ENTRY(11, 1, 1), TC_ENTRY(11, 2, 1), TC_ENTRY(15, 1, 2),
@@ -1638,22 +1612,16 @@ static const KernelEntry* find_kernel(int K, int S, int D)
     return nullptr;
 }
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_FIXED = 1024 /*barriers*/ + MAX_CO_CTA * 4 /*BN shift*/;
 
-// back-off of the waiting roles in ns (window producer, weight producer, MMA issuer, epilogue); VASR_TC_SPIN=a,b,c,d
-// overrides.  Default 0 = plain try_wait loop: the sweep in profiles/r1_v10_spin_sweep.log shows no gain from parking
-// the waiting warps (try_wait already suspends them), and a sleeping MMA issuer or epilogue adds its wake-up latency
-// to every chunk of the latency-mode tiles.
-static void spin_defaults(int (&spin)[4])
-{
-    static int v[4] = {-1, 0, 0, 0};
-    if (v[0] < 0) {
-        int d[4] = {0, 0, 0, 0};
-        const char* e = getenv("VASR_TC_SPIN");
-        if (e) sscanf(e, "%d,%d,%d,%d", &d[0], &d[1], &d[2], &d[3]);
-        for (int i = 0; i < 4; ++i) v[i] = d[i] < 0 ? 0 : d[i];
-    }
-    for (int i = 0; i < 4; ++i) spin[i] = v[i];
-}
+// Developer switches (libvasr_b200_dev.so only; the product library has no environment switches on this path):
+//   VASR_TC_PROF=1 role cycle counters, VASR_TC_DBG=bits ablations, VASR_TC_PAIR=0 single-CTA 128-row kernel instead
+//   of the pair kernel, VASR_TC_LAT=0 no 32-row latency tiles, VASR_TC_RINGS=x,b,a ring depths of the pair kernel.
+#ifdef VASR_DEV
+static int dev_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+static constexpr int dev_env(const char*, int dflt) { return dflt; }
+#endif
 
 static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_off, int* stage_bytes, int tn = TN)
 {
@@ -1667,22 +1635,36 @@ static void x_geometry(int K, int S, int D, int* n_xbox, int* xbox_rows, int* w_
     *stage_bytes = (bytes + 1023) / 1024 * 1024;
 }
 
-// ring depths under the 227 KiB budget.  The tensor-core side (weight TMA latency + MMA) is the critical path
-// (profiles/), so the weight ring gets the capacity: 2 activation-window stages (3 when there is room), 2
-// activation-operand stages, and as many 256-channel weight slots as fit (at least one chunk, at most four chunks).
+// ring depths of the single-CTA kernels under the 227 KiB budget: 2 activation-window stages (3 when there is room), 2
+// activation-operand stages (3 when there is room), and as many 256-channel weight slots as fit (at most four chunks).
 static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int* xstages, int* bstages, int* aslots)
 {
     const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
-    const int overhead = 1024 /*barriers*/ + MAX_CO_CTA * 4 /*BN shift*/ + epi_bytes;
+    const int overhead = SMEM_FIXED + epi_bytes;
     int xs = 2, bs = 2;
     int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
     if (slots > 4 * nN) slots = 4 * nN;
     if (slots > 16) slots = 16;
-    // spend what is left on a third activation-window stage, then a third operand stage
     int left = SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes - slots * w_slot;
     if (left >= x_stage_bytes) { xs = 3; left -= x_stage_bytes; }
     if (left >= b_stage) { bs = 3; left -= b_stage; }
     *xstages = xs; *bstages = bs; *aslots = slots;
+}
+// ring depths of the pair kernel: each depthwise group holds a window stage while it computes, so a third stage is what
+// lets the loads run ahead (with two, every chunk exposes its TMA latency); three operand stages let the depthwise
+// warps work through the accumulator drain at the end of a tile; the rest goes to 16 KiB (half-block) weight slots.
+static bool pick_rings_pair(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots)
+{
+    const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart;
+    const int overhead = SMEM_FIXED + 4 * EPI_SUB_BYTES;
+    int xs = 3, bs = 3;
+    int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
+    if (slots < nN) { bs = 2; slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot; }
+    if (slots < nN) return false;
+    if (slots > 4 * nN) slots = 4 * nN;
+    if (slots > 16) slots = 16;
+    *xstages = xs; *bstages = bs; *aslots = slots;
+    return true;
 }
 
 }  // namespace tc
@@ -1698,18 +1680,17 @@ int tc_init()
     VASR_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess)
         return set_error(VASR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    g_encode = (EncodeTiledFn)fn;
     int dev = 0;
     VASR_CUDA_OK(cudaGetDevice(&dev));
     VASR_CUDA_OK(cudaDeviceGetAttribute(&tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     for (const KernelEntry& e : g_kernels)
         for (int i = 0; i < 2; ++i)
-            for (int j = 0; j < 2; ++j)
-                VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    const void* seg_fns[] = {(const void*)segment_kernel<2, 4, 128>, (const void*)segment_kernel<1, 4, 128>,
-                             (const void*)segment_kernel<2, 8, 128>, (const void*)segment_kernel<1, 8, 128>,
-                             (const void*)segment_kernel<2, 4, 32>, (const void*)segment_kernel<1, 4, 32>};
+            VASR_CUDA_OK(cudaFuncSetAttribute(e.fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    const void* seg_fns[] = {(const void*)segment_kernel<2, 128>, (const void*)segment_kernel<1, 128>,
+                             (const void*)segment_kernel<2, 32>, (const void*)segment_kernel<1, 32>,
+                             (const void*)segment_pair_kernel<2>, (const void*)segment_pair_kernel<1>};
     for (const void* f : seg_fns) VASR_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    g_encode = (EncodeTiledFn)fn;
     return VASR_OK;
 }
 
@@ -1725,7 +1706,7 @@ bool subblock_tc_supported(const SubBlock& sb)
     return true;
 }
 
-// weights: per-output-channel power-of-two pre-scale, fp16 hi/lo split, TMA maps
+// weights: one power-of-two pre-scale per layer, fp16 hi/lo split, TMA maps
 int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, const float* dw_kc,
                      std::vector<void*>& allocs)
 {
@@ -1794,6 +1775,34 @@ int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, cons
     return VASR_OK;
 }
 
+#ifdef VASR_DEV
+// role cycle counters of the last launch (developer builds): [32] device words, printed after a stream sync
+static unsigned long long* dev_prof_buffer(cudaStream_t st)
+{
+    static int on = -1;
+    static unsigned long long* d = nullptr;
+    if (on < 0) {
+        on = tc::dev_env("VASR_TC_PROF", 0) > 0 ? 1 : 0;
+        if (on && cudaMalloc(&d, 32 * sizeof(unsigned long long)) != cudaSuccess) on = 0;
+    }
+    if (!on) return nullptr;
+    cudaMemsetAsync(d, 0, 32 * sizeof(unsigned long long), st);
+    return d;
+}
+static void dev_prof_print(const char* head, const unsigned long long* d, cudaStream_t st, bool pair)
+{
+    unsigned long long h[32];
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    const double n = (double)(h[15] ? h[15] : 1);
+    fprintf(stderr, "%s | dw: wait_x %.0f comp %.0f wait_b %.0f store %.0f | xprod wait %.0f dep %.0f | aprod wait %.0f | mma: wait_b %.0f wait_a %.0f wait_acc %.0f issue %.0f | epi: wait %.0f drain %.0f (kcycles per CTA)\n",
+            head, h[0] / n / 1e3, h[1] / n / 1e3, h[2] / n / 1e3, h[3] / n / 1e3, h[4] / n / 1e3, h[5] / n / 1e3, h[12] / n / 1e3,
+            h[6] / n / 1e3, h[7] / n / 1e3, h[8] / n / 1e3, h[9] / n / 1e3, h[10] / n / 1e3, h[11] / n / 1e3);
+    if (pair)
+        fprintf(stderr, "   peer CTA | dw group 1: wait_x %.0f comp %.0f wait_b %.0f store %.0f | epi: wait %.0f drain %.0f | xprod wait %.0f dep %.0f\n",
+                h[16] / n / 1e3, h[17] / n / 1e3, h[18] / n / 1e3, h[19] / n / 1e3, h[20] / n / 1e3, h[21] / n / 1e3, h[22] / n / 1e3, h[23] / n / 1e3);
+}
+#endif
+
 int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const float* res_in, long long r_bstride,
                        float* y, long long y_bstride, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
@@ -1819,13 +1828,13 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
     // TMA-store epilogue when its 32 KiB of staging still leaves one chunk of weight slots; direct stores otherwise
     p.tma_epi = 1;
     pick_rings(npart, p.x_stage_bytes, p.nN, 2 * EPI_STAGE_BYTES, &p.xstages, &p.bstages, &p.aslots);
-    if (p.aslots < p.nN || getenv("VASR_TC_NO_TMA_EPI")) {
+    if (p.aslots < p.nN) {
         p.tma_epi = 0;
         pick_rings(npart, p.x_stage_bytes, p.nN, 0, &p.xstages, &p.bstages, &p.aslots);
     }
     if (p.aslots < p.nN) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded (k=%d)", K);
     const size_t smem = (size_t)p.aslots * W_PART * npart + (size_t)p.bstages * PART_BYTES * npart +
-                        (size_t)p.xstages * p.x_stage_bytes + 1024 + MAX_CO_CTA * 4 + (p.tma_epi ? 2 * EPI_STAGE_BYTES : 0);
+                        (size_t)p.xstages * p.x_stage_bytes + SMEM_FIXED + (p.tma_epi ? 2 * EPI_STAGE_BYTES : 0);
     p.b0 = b0;
     // activation tensor maps cover the whole batch and are cached per layer (pointers/shapes rarely change)
     int rc;
@@ -1852,43 +1861,41 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
     dim3 grid(n_tiles < max_ctas ? n_tiles : max_ctas, 1, 1);
     void* args[] = {(void*)sb.tm_x, (void*)(sb.has_res ? sb.tm_r : sb.tm_x), (void*)sb.tm_w_hi, (void*)sb.tm_w_lo,
                     (void*)sb.tm_r_hi, (void*)sb.tm_r_lo, (void*)sb.tm_y, (void*)&p};
-    static int prof_on = -1;
-    static unsigned long long* d_prof = nullptr;
-    if (prof_on < 0) {
-        const char* e = getenv("VASR_TC_PROF");
-        prof_on = (e && atoi(e) > 0) ? 1 : 0;
-        if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
-    }
-    p.prof = prof_on ? d_prof : nullptr;
-    spin_defaults(p.spin);
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
-    if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
-    // depthwise warps per CTA: 4 (16 outputs per thread) by default, VASR_TC_NDW=8 selects the 8-warp variant
-    static int ndw = -1;
-    if (ndw < 0) { const char* e = getenv("VASR_TC_NDW"); ndw = (e && atoi(e) == 8) ? 8 : 4; }
-    VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1][ndw == 8 ? 0 : 1], grid, dim3(nthreads(ndw)), args, smem, st));
+#ifdef VASR_DEV
+    p.prof = dev_prof_buffer(st);
+    p.dbg = dev_env("VASR_TC_DBG", 0);
+#endif
+    VASR_CUDA_OK(cudaLaunchKernel(ke->fn[split3 ? 0 : 1], grid, dim3(NTHREADS), args, smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    if (prof_on) {
-        unsigned long long h[16];
-        VASR_CUDA_OK(cudaStreamSynchronize(st));
-        VASR_CUDA_OK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
-        const double n = (double)(h[15] ? h[15] : 1);
-        fprintf(stderr, "TCPROF k=%d cin=%d cout=%d res=%d tiles=%d ctas=%d xs=%d bs=%d as=%d | dw: wait_x %.0f comp %.0f wait_b %.0f store %.0f | xprod wait %.0f | aprod wait %.0f | mma: wait_b %.0f wait_a %.0f wait_acc %.0f issue %.0f | epi: wait %.0f drain %.0f (kcycles per CTA)\n",
-                K, sb.cin, sb.cout, (int)sb.has_res, n_tiles, (int)grid.x, p.xstages, p.bstages, p.aslots,
-                h[0] / n / 1e3, h[1] / n / 1e3, h[2] / n / 1e3, h[3] / n / 1e3, h[4] / n / 1e3, h[5] / n / 1e3,
-                h[6] / n / 1e3, h[7] / n / 1e3, h[8] / n / 1e3, h[9] / n / 1e3, h[10] / n / 1e3, h[11] / n / 1e3);
+#ifdef VASR_DEV
+    if (p.prof) {
+        char head[160];
+        snprintf(head, sizeof(head), "TCPROF k=%d cin=%d cout=%d res=%d tiles=%d ctas=%d xs=%d bs=%d as=%d", K, sb.cin, sb.cout,
+                 (int)sb.has_res, n_tiles, (int)grid.x, p.xstages, p.bstages, p.aslots);
+        dev_prof_print(head, p.prof, st, false);
     }
+#endif
     return VASR_OK;
 }
 
 // ------------------------------------------------------------------------------------------ segment launch
 
-struct SegCacheEntry {
-    unsigned long long uid; int n; const void* x_first; const void* y_last; int B, T, tr;
-    tc::LayerDesc* d_desc;
-    int x_stage_bytes;
+// Device descriptor tables (tensor maps + per-layer scalars) are cached.  The key holds EVERYTHING a table is built
+// from: each layer's identity, its input / residual / output pointers with their batch strides (the strides depend on
+// T_f, the segment's T does not: T_f = 2k and 2k - 1 give the same T) and its length table, plus batch, frames and the
+// kernel variant.
+struct SegLayerKey {
+    unsigned long long uid; const void* x; const void* res; const void* y; const void* len_out; long long xs, rs, ys;
+    bool operator==(const SegLayerKey& o) const
+    {
+        return uid == o.uid && x == o.x && res == o.res && y == o.y && len_out == o.len_out && xs == o.xs && rs == o.rs && ys == o.ys;
+    }
 };
-static std::vector<SegCacheEntry> g_seg_cache;   // device descriptor tables, keyed by (model layer, buffers, shape)
+struct SegCacheEntry {
+    std::vector<SegLayerKey> key; int B, T, variant;
+    tc::LayerDesc* d_desc;
+};
+static std::vector<SegCacheEntry> g_seg_cache;
 
 bool segment_tc_layer_ok(const SubBlock& sb)
 {
@@ -1900,40 +1907,52 @@ bool segment_tc_layer_ok(const SubBlock& sb)
     return true;
 }
 
-// two-group variant (VASR_TC_ALT): each group holds a window stage while it computes, so it only pays off with a third
-// stage to prefetch into (measured: with 2 stages the exposed window-load latency eats the whole gain).  Ring choice
-// for it: 3 window stages, 3 operand stages, and at least two chunks of weight slots; *alt = 0 when that does not fit
-// (the 512-channel layers at K >= 51) and the one-group kernel is used instead.
-static int alt_requested()
+// how a run of layers is executed for a given sub-batch shape
+struct SegPlan {
+    int tr;                  // valid rows per tile: 128, or 32 (latency mode)
+    bool pair;               // CTA-pair kernel (cta_group::2)
+    int x_stage_bytes, xstages, bstages, aslots;
+    size_t smem;
+};
+static int seg_x_stage_bytes(const SegLayer* L, int n, int tr)
 {
-    static int alt = -1;
-    if (alt < 0) { const char* e = getenv("VASR_TC_ALT"); alt = (e && atoi(e) > 0) ? atoi(e) : 0; }
-    return alt;
-}
-static void seg_geometry(const SegLayer* L, int n, int npart, int* x_stage_bytes, int* xstages, int* bstages, int* aslots,
-                         int* alt = nullptr, int tr = tc::TN)
-{
-    using namespace tc;
     int mx = 0;
     for (int i = 0; i < n; ++i) {
         int nb, br, wo, sbytes;
-        x_geometry(L[i].sb->kernel, 1, 1, &nb, &br, &wo, &sbytes, tr);
+        tc::x_geometry(L[i].sb->kernel, 1, 1, &nb, &br, &wo, &sbytes, tr);
         if (sbytes > mx) mx = sbytes;
     }
-    *x_stage_bytes = mx;
+    return mx;
+}
+static bool plan_segment(const SegLayer* L, int n, int npart, int T, int nb, SegPlan* pl)
+{
+    using namespace tc;
     const int nN = L[0].sb->cout / 256;
-    pick_rings(npart, mx, nN, 2 * EPI_STAGE_BYTES, xstages, bstages, aslots);
-    if (alt) {
-        *alt = 0;
-        if (tr != TN) return;
-        if (alt_requested() == 2) *alt = 1;                       // 2: force the two-group kernel with the default rings
-        else if (alt_requested() == 1) {
-            const int w_slot = W_PART * npart, b_stage = PART_BYTES * npart;
-            const int overhead = 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
-            const int slots = (SMEM_LIMIT - overhead - 3 * b_stage - 3 * mx) / w_slot;
-            if (slots >= 2 * nN) { *alt = 1; *xstages = 3; *bstages = 3; *aslots = slots > 4 * nN ? 4 * nN : slots; }
+    // latency mode: when the 128-row tiles of a layer would occupy less than half of the SMs, use 32-row tiles
+    const bool lat = dev_env("VASR_TC_LAT", 1) != 0 && T > 0 && ceil_div(T, TN) * nb * 2 <= g_num_sms;
+    pl->tr = lat ? 32 : TN;
+    pl->pair = false;
+    pl->x_stage_bytes = seg_x_stage_bytes(L, n, pl->tr);
+    if (!lat && dev_env("VASR_TC_PAIR", 1) != 0 && g_num_sms >= 2 &&
+        pick_rings_pair(npart, pl->x_stage_bytes, nN, &pl->xstages, &pl->bstages, &pl->aslots)) {
+        pl->pair = true;
+#ifdef VASR_DEV
+        if (const char* e = getenv("VASR_TC_RINGS")) {
+            int xs = 0, bs = 0, as = 0;
+            if (sscanf(e, "%d,%d,%d", &xs, &bs, &as) == 3 && xs >= 2 && xs <= MAX_STAGES && bs >= 2 && bs <= MAX_STAGES && as >= nN && as <= 16 &&
+                (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED + 4 * EPI_SUB_BYTES <= (size_t)SMEM_LIMIT) {
+                pl->xstages = xs; pl->bstages = bs; pl->aslots = as;
+            }
         }
+#endif
+        pl->smem = (size_t)pl->aslots * W_HALF * npart + (size_t)pl->bstages * PART_BYTES * npart +
+                   (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED + 4 * EPI_SUB_BYTES;
+        return true;
     }
+    pick_rings(npart, pl->x_stage_bytes, nN, 2 * EPI_STAGE_BYTES, &pl->xstages, &pl->bstages, &pl->aslots);
+    pl->smem = (size_t)pl->aslots * W_PART * npart + (size_t)pl->bstages * PART_BYTES * npart +
+               (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED + 2 * EPI_STAGE_BYTES;
+    return pl->aslots >= nN;
 }
 
 bool segment_tc_ok(const SegLayer* L, int n, int split3)
@@ -1944,8 +1963,9 @@ bool segment_tc_ok(const SegLayer* L, int n, int split3)
         if (!segment_tc_layer_ok(*L[i].sb)) return false;
         if (L[i].sb->cout != L[0].sb->cout) return false;
     }
-    int xsb, xs, bs, as;
-    seg_geometry(L, n, split3 ? 2 : 1, &xsb, &xs, &bs, &as);
+    // every variant must be able to run the segment: the single-CTA 128-row rings are the tightest
+    int xs, bs, as;
+    pick_rings(split3 ? 2 : 1, seg_x_stage_bytes(L, n, TN), L[0].sb->cout / 256, 2 * EPI_STAGE_BYTES, &xs, &bs, &as);
     return as >= L[0].sb->cout / 256;
 }
 
@@ -1955,31 +1975,21 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     using namespace tc;
     if (!segment_tc_ok(L, n, split3)) return set_error(VASR_EINVAL, "tcgen05 path: layers do not form a segment");
     const int npart = split3 ? 2 : 1;
+    SegPlan pl{};
+    if (!plan_segment(L, n, npart, T, nb, &pl)) return set_error(VASR_EINVAL, "tcgen05 path: shared memory budget exceeded for the segment");
+    const int tr = pl.tr;
+    const bool pair = pl.pair;
     SegParams p{};
-    // latency mode: when the 128-row tiles of a layer would occupy less than half of the SMs, use 32-row tiles
-    // (VASR_TC_LAT=0 switches it off)
-    static int lat_on = -1;
-    if (lat_on < 0) { const char* e = getenv("VASR_TC_LAT"); lat_on = (e && atoi(e) == 0) ? 0 : 1; }
-    const int tr = (lat_on && ceil_div(T, TN) * nb * 2 <= g_num_sms) ? 32 : TN;
-    int alt = 0;
-    seg_geometry(L, n, npart, &p.x_stage_bytes, &p.xstages, &p.bstages, &p.aslots, &alt, tr);
+    p.x_stage_bytes = pl.x_stage_bytes; p.xstages = pl.xstages; p.bstages = pl.bstages; p.aslots = pl.aslots;
     p.nN = L[0].sb->cout / 256;
-    // VASR_TC_PAIR=1 (experimental, not validated on the GPU yet): CTA-pair kernel with cta_group::2 MMAs where the
-    // layer's tile count is even and three window + three operand stages fit next to 16 KiB weight slots
-    static int pair_on = -1;
-    if (pair_on < 0) { const char* e = getenv("VASR_TC_PAIR"); pair_on = (e && atoi(e) > 0) ? 1 : 0; }
-    int pair = 0;
-    if (pair_on && tr == TN && ((ceil_div(T, TN) * nb) % 2) == 0) {
-        const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart;
-        const int overhead = 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
-        const int slots = (SMEM_LIMIT - overhead - 3 * b_stage - 3 * p.x_stage_bytes) / w_slot;
-        if (slots >= p.nN) { pair = 1; alt = 0; p.xstages = 3; p.bstages = 3; p.aslots = slots > 4 * p.nN ? 4 * p.nN : slots; }
-    }
-    const int variant = pair ? 256 : tr;                      // key of the descriptor cache (weight boxes differ)
-    // descriptor table (tensor maps + per-layer scalars) in device memory, cached per (layer, buffers, shape)
+    const int variant = pair ? 256 : tr;                      // key of the descriptor cache (weight / output boxes differ)
+    std::vector<SegLayerKey> key((size_t)n);
+    for (int i = 0; i < n; ++i)
+        key[i] = SegLayerKey{L[i].sb->uid, L[i].x, L[i].sb->has_res ? L[i].res : nullptr, L[i].y, L[i].len_out, L[i].xs,
+                             L[i].sb->has_res ? L[i].rs : 0, L[i].ys};
     LayerDesc* d_desc = nullptr;
     for (const SegCacheEntry& e : g_seg_cache)
-        if (e.uid == L[0].sb->uid && e.n == n && e.x_first == L[0].x && e.y_last == L[n - 1].y && e.B == B && e.T == T && e.tr == variant) { d_desc = e.d_desc; break; }
+        if (e.B == B && e.T == T && e.variant == variant && e.key == key) { d_desc = e.d_desc; break; }
     if (!d_desc) {
         std::vector<LayerDesc> h((size_t)n);
         int rc;
@@ -1999,11 +2009,12 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
                     if ((rc = encode_w(&d.tm_r_hi, (const __half*)sb.res_h, sb.cout, sb.res_cin, 128))) return rc;
                     if ((rc = encode_w(&d.tm_r_lo, (const __half*)sb.res_l, sb.cout, sb.res_cin, 128))) return rc;
                 } else { d.tm_r_hi = d.tm_w_hi; d.tm_r_lo = d.tm_w_lo; }
+                if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, TN, EPI_SUB_COLS))) return rc;
             } else {
                 memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
                 memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
+                if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, tr))) return rc;
             }
-            if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, tr))) return rc;
             d.dw_w = sb.dw_tc; d.shift = sb.shift; d.len_out = L[i].len_out; d.wscale_inv = sb.wscale_inv_scalar;
             d.K = sb.kernel; d.n_main = sb.cin / KC; d.n_res = sb.has_res ? sb.res_cin / KC : 0;
             d.relu = sb.relu ? 1 : 0; d.mask_tail = 1; d.pad = sb.pad;
@@ -2015,55 +2026,43 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
         }
         VASR_CUDA_OK(cudaMalloc((void**)&d_desc, sizeof(LayerDesc) * (size_t)n));
         VASR_CUDA_OK(cudaMemcpy(d_desc, h.data(), sizeof(LayerDesc) * (size_t)n, cudaMemcpyHostToDevice));
-        g_seg_cache.push_back(SegCacheEntry{L[0].sb->uid, n, L[0].x, L[n - 1].y, B, T, variant, d_desc, p.x_stage_bytes});
+        g_seg_cache.push_back(SegCacheEntry{key, B, T, variant, d_desc});
     }
     p.layers = d_desc; p.n_layers = n;
     p.tile_counter = tile_counter; p.done = done; p.done_stride = done_stride;
     p.T_out = T; p.b0 = b0; p.n_tt = ceil_div(T, tr); p.n_utt = nb;
-    const size_t smem = (size_t)p.aslots * (pair ? W_HALF : W_PART) * npart + (size_t)p.bstages * PART_BYTES * npart +
-                        (size_t)p.xstages * p.x_stage_bytes + 1024 + MAX_CO_CTA * 4 + 2 * EPI_STAGE_BYTES;
-    const long long n_items = (long long)p.n_tt * p.n_utt * n;          // tiles; the pair kernel takes two per item
+    const long long tpl = (long long)p.n_tt * p.n_utt;
+    const long long n_items = (pair ? (tpl + 1) / 2 : tpl) * n;         // work items: tiles, or pairs of tiles
     int max_ctas = g_num_sms;
     if (grid_limit > 0 && grid_limit < max_ctas) max_ctas = grid_limit;
-    if (pair) max_ctas &= ~1;
-    dim3 grid((unsigned)(n_items < max_ctas ? n_items : max_ctas), 1, 1);
-    static int prof_on = -1;
-    static unsigned long long* d_prof = nullptr;
-    if (prof_on < 0) {
-        const char* e = getenv("VASR_TC_PROF");
-        prof_on = (e && atoi(e) > 0) ? 1 : 0;
-        if (prof_on) VASR_CUDA_OK(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    unsigned grid_x;
+    if (pair) {
+        long long clusters = max_ctas / 2;
+        if (clusters < 1) clusters = 1;
+        if (n_items < clusters) clusters = n_items;
+        grid_x = (unsigned)(2 * clusters);
+    } else {
+        grid_x = (unsigned)(n_items < max_ctas ? n_items : max_ctas);
     }
-    p.prof = prof_on ? d_prof : nullptr;
-    spin_defaults(p.spin);
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("VASR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
-    if (prof_on) VASR_CUDA_OK(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st));
+    dim3 grid(grid_x, 1, 1);
+#ifdef VASR_DEV
+    p.prof = dev_prof_buffer(st);
+    p.dbg = dev_env("VASR_TC_DBG", 0);
+#endif
     void* args[] = {(void*)&p};
-    // VASR_TC_ALT: two depthwise groups on alternate chunks (segment_kernel<., 8>) where the rings allow it
-    if (pair) {                                               // experimental kernel: its attributes are set on first use only
-        static bool pair_attr = false;
-        if (!pair_attr) {
-            VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-            VASR_CUDA_OK(cudaFuncSetAttribute((const void*)segment_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-            pair_attr = true;
-        }
-    }
     const void* fn = pair     ? (split3 ? (const void*)segment_pair_kernel<2> : (const void*)segment_pair_kernel<1>)
-                     : tr != TN ? (split3 ? (const void*)segment_kernel<2, 4, 32> : (const void*)segment_kernel<1, 4, 32>)
-                     : alt    ? (split3 ? (const void*)segment_kernel<2, 8, 128> : (const void*)segment_kernel<1, 8, 128>)
-                              : (split3 ? (const void*)segment_kernel<2, 4, 128> : (const void*)segment_kernel<1, 4, 128>);
-    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(pair ? PAIR_THREADS : seg_threads(alt ? 8 : 4)), args, smem, st));
+                     : tr != TN ? (split3 ? (const void*)segment_kernel<2, 32> : (const void*)segment_kernel<1, 32>)
+                              : (split3 ? (const void*)segment_kernel<2, 128> : (const void*)segment_kernel<1, 128>);
+    VASR_CUDA_OK(cudaLaunchKernel(fn, grid, dim3(pair ? PAIR_THREADS : NTHREADS), args, pl.smem, st));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    if (prof_on) {
-        unsigned long long h[16];
-        VASR_CUDA_OK(cudaStreamSynchronize(st));
-        VASR_CUDA_OK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
-        const double c = (double)(h[15] ? h[15] : 1);
-        fprintf(stderr, "TCSEG layers=%d k=%d..%d cout=%d items=%lld ctas=%d xs=%d bs=%d as=%d | dw: wait_x %.0f comp %.0f wait_b %.0f store %.0f | xprod wait %.0f dep %.0f | aprod wait %.0f | mma: wait_b %.0f wait_a %.0f wait_acc %.0f issue %.0f | epi: wait %.0f drain %.0f (kcycles per CTA)\n",
-                n, L[0].sb->kernel, L[n - 1].sb->kernel, L[0].sb->cout, n_items, (int)grid.x, p.xstages, p.bstages, p.aslots,
-                h[0] / c / 1e3, h[1] / c / 1e3, h[2] / c / 1e3, h[3] / c / 1e3, h[4] / c / 1e3, h[5] / c / 1e3, h[12] / c / 1e3,
-                h[6] / c / 1e3, h[7] / c / 1e3, h[8] / c / 1e3, h[9] / c / 1e3, h[10] / c / 1e3, h[11] / c / 1e3);
+#ifdef VASR_DEV
+    if (p.prof) {
+        char head[200];
+        snprintf(head, sizeof(head), "TCSEG%s layers=%d k=%d..%d cout=%d items=%lld ctas=%d tr=%d xs=%d bs=%d as=%d", pair ? "(pair)" : "", n,
+                 L[0].sb->kernel, L[n - 1].sb->kernel, L[0].sb->cout, n_items, (int)grid.x, tr, p.xstages, p.bstages, p.aslots);
+        dev_prof_print(head, p.prof, st, pair);
     }
+#endif
     return VASR_OK;
 }
 
