@@ -60,7 +60,7 @@ if __name__ == "__main__":
             os.remove(out)
         print(f"[{name}] {envs}", flush=True)
         try:
-            r = subprocess.run([sys.executable, __file__, "--child", str(B), str(secs), out], env=env, timeout=180,
+            r = subprocess.run([sys.executable, __file__, "--child", str(B), str(secs), out], env=env, timeout=100,
                                stderr=subprocess.STDOUT, stdout=subprocess.PIPE, text=True)
             txt = r.stdout
             rc = r.returncode

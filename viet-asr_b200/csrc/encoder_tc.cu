@@ -78,7 +78,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     // try_wait suspends the warp in hardware for a bounded time; parking the waiting roles with nanosleep on top of
     // it was measured to make no difference (profiles/r1_v10_spin_sweep.log)
-    while (!mbar_try(bar, parity)) {}
+    // (watchdog: a barrier that never completes - a protocol error - traps instead of hanging the device)
+    unsigned spins = 0;
+    while (!mbar_try(bar, parity)) { if (++spins > (1u << 28)) __trap(); }
 }
 __device__ __forceinline__ void fence_barrier_init()
 {
@@ -701,6 +703,8 @@ struct alignas(128) LayerDesc {
     const float* dw_w;       // [Cin/32][K][32]
     const float* shift;      // [Cout]
     const int* len_out;      // [B]
+    float* out;              // [B, T, Cout] output with an explicit batch stride (elements): direct stores of the pair kernel
+    long long out_bstride;
     float wscale_inv;
     int K, n_main, n_res, relu, mask_tail, pad;
     int n_xbox, xbox_rows, x_w_off;
@@ -726,6 +730,16 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p)
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// cross-layer dependency wait with a watchdog (~seconds): a protocol error must end in a launch failure that the
+// host reports, never in a hung GPU
+__device__ __forceinline__ void dep_wait(const int* flag, int need)
+{
+    unsigned spins = 0;
+    while (ld_acquire_gpu(flag) < need) {
+        __nanosleep(40);
+        if (++spins > (1u << 26)) __trap();
+    }
+}
 
 #define SEG_K_SWITCH(Kv, STMT)                                   \
     switch (Kv) {                                                \
@@ -835,7 +849,7 @@ segment_kernel(const SegParams p)
                     const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
                     const int need = 2 * p.n_tt;
                     PROF_BEGIN();
-                    while (ld_acquire_gpu(flag) < need) __nanosleep(40);
+                    dep_wait(flag, need);
                     PROF_ADD(1);
                     fence_proxy_async_all();        // the TMA (async proxy) reads below are ordered after the acquire
                 }
@@ -1120,7 +1134,9 @@ segment_kernel(const SegParams p)
 // stores, epilogue - but the 1x1 convolutions are issued by the leader as tcgen05.mma.cta_group::2 (M = 256 over both
 // SMs): the weight block of an instruction (256 output channels x 32 input channels) is split between the CTAs, so a
 // weight slot is 16 KiB instead of 32, every SM streams half of the weights from L2 and the tensor core of each SM
-// reads half of the B operand.  The 32 KiB saved pay for the third window stage that the two-group depthwise needs.
+// reads half of the B operand.  The shared memory saved - and the 32 KiB of store staging that the register-direct
+// epilogue does not need - pay for the third window stage that the two-group depthwise needs and for deeper weight
+// prefetch.
 //
 // Depthwise: 8 warps in two groups (warps 0-3 / 4-7) that take alternate chunks, i.e. two depthwise warps per SM
 // sub-partition whose FMA streams fill each other's stalls and fp16-split/store phases.  The kernel starts at 96
@@ -1137,6 +1153,8 @@ segment_kernel(const SegParams p)
 //   empty_b, empty_a, acc_full              released in both CTAs by tcgen05.commit ... multicast::cluster (mask 0b11)
 //   L:full_a[slot]    both CTAs' weight TMA loads (cp.async.bulk.tensor ... cta_group::2) complete on it
 //   L:acc_empty       16 arrivals: the epilogue warps of both CTAs
+// Layer-to-layer hand-over: every epilogue warp bumps the (layer, utterance) counter after its stores (release at gpu
+// scope); a tile of the next layer starts once all NEPI x n_tt warps of the utterance's previous layer have done so.
 // Remote arrives use the default (release.cta) semantics like CUTLASS's ClusterBarrier::arrive: what they publish is
 // either consumed by the arriving CTA's own tensor core (operand stage: generic-proxy stores + fence.proxy.async in
 // the writing CTA) or is no data at all (accumulator drained).  A cluster-scope release costs a MEMBAR.ALL.GPU per
@@ -1184,23 +1202,22 @@ __device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar)          // ar
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16])
+// 16 lanes x 256 bit, x4: rows (lane/4, lane/4 + 8) x columns 8j + 2(lane%4) + {0,1}, j = 0..3 -> r[4j + {0,1}] (row lane/4),
+// r[4j + {2,3}] (row lane/4 + 8)   (cute SM100_TMEM_LOAD_16dp256b4x)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // D = f32, A = B = f16, both K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
 constexpr uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr int W_HALF = 128 * KC * 2;            // this CTA's half of a weight block: [128 co x 64 B] fp16 = 8 KiB per part
 constexpr int PAIR_THREADS = 640;
-constexpr int EPI_SUB_COLS = 16;                // output channels per epilogue sub-slice (64-byte rows, SWIZZLE_64B)
-constexpr int EPI_SUB_BYTES = TN * EPI_SUB_COLS * 4;          // 8 KiB; two per epilogue half-group = 32 KiB in all
 
 template <int NPART>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
@@ -1215,8 +1232,7 @@ segment_pair_kernel(const SegParams p)
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
     unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
-    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;      // [2 halves][2][128 rows x 64 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 4 * EPI_SUB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + (size_t)p.xstages * p.x_stage_bytes);
     const int XSTAGES = p.xstages, BSTAGES = p.bstages;
     uint64_t* full_x = bars;
     uint64_t* empty_x = full_x + MAX_STAGES;
@@ -1278,11 +1294,11 @@ segment_pair_kernel(const SegParams p)
                 decode(item, l, b, t0, dup);
                 const LayerDesc* L = p.layers + l;
                 if (l > 0) {
-                    // every tile of layer l-1 of this utterance has been stored (both epilogue halves of each time tile)
+                    // every tile of layer l-1 of this utterance has been stored (all eight epilogue warps of each time tile)
                     const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
-                    const int need = 2 * p.n_tt;
+                    const int need = NEPI * p.n_tt;
                     PROF_BEGIN();
-                    while (ld_acquire_gpu(flag) < need) __nanosleep(40);
+                    dep_wait(flag, need);
                     PROF_ADD(1);
                     fence_proxy_async_all();        // the TMA (async proxy) reads below are ordered after the acquire
                 }
@@ -1380,19 +1396,24 @@ segment_pair_kernel(const SegParams p)
             }
         }
     } else if (warp >= WARP_EPI) {
-        // ======== epilogue of this CTA's 128 rows: TMEM -> +shift, ReLU, mask -> smem staging -> TMA store ========
-        // 16-column sub-slices through two 8 KiB staging buffers per half-group: the TMA store of sub-slice i reads its
-        // buffer while sub-slice i+1 is loaded from TMEM and written into the other one.
+        // ======== epilogue of this CTA's 128 rows: TMEM -> +shift, ReLU, mask -> global memory, no staging ========
+        // tcgen05.ld.16x256b hands a warp the accumulator in the classic 16 x 8 fragment layout: thread t holds rows
+        // t/4 and t/4 + 8, columns 2(t%4), 2(t%4)+1 of every 8-column block.  A warp-wide 8-byte store therefore
+        // writes eight full 32-byte sectors (8 rows x 8 channels): sector-exact global writes straight from
+        // registers - no shared-memory staging, no TMA store, no barriers between the epilogue warps.  Each warp drains
+        // its 32 rows x 256 columns (its half of every N block) in 16 loads of 16 registers, software-pipelined so
+        // that the next TMEM load is in flight while the current fragment is finished and stored.
         const int q = warp & 3;
         const int half = (warp - WARP_EPI) >> 2;
-        const int row = q * 32 + lane;
-        const bool issuer = (q == 0 && lane == 0);
-        unsigned char* stage = epi_stage + half * 2 * EPI_SUB_BYTES;
+        const int r0 = lane >> 2;                              // row within a 16-row block (this thread also owns r0 + 8)
+        const int c2 = (lane & 3) * 2;                         // column pair within an 8-column block
         const uint32_t acc_empty_leader = mapa_u32(acc_empty, 0);
-        const int nsub = p.nN * (128 / EPI_SUB_COLS);
-        const uint32_t row_off = (uint32_t)row * 64u, row_sw = ((uint32_t)row >> 1) & 3u;
+        const int nblk = p.nN * 4;                             // 32-column blocks of this half-group per tile
+        const int nstep = 2 * nblk;                            // x two 16-row halves of the warp's lane quarter
+        const int Cout = p.nN * 256;
         int cur_l = -1;
         float wsc = 1.f; int relu = 0; const int* len_out = nullptr;
+        float* out_base = nullptr; long long out_bstride = 0;
         int ab = 0; uint32_t accph = 0;
         for (int item = item0; item < n_items; item += item_step) {
             int l, b, t0; bool dup;
@@ -1402,62 +1423,73 @@ segment_pair_kernel(const SegParams p)
                 named_bar_sync(3, NEPI * 32);
                 const float* shift = L->shift;
                 for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI * 32) ep_shift[i] = __ldg(shift + i);
-                wsc = L->wscale_inv; relu = L->relu; len_out = L->len_out;
+                wsc = L->wscale_inv; relu = L->relu; len_out = L->len_out; out_base = L->out; out_bstride = L->out_bstride;
                 named_bar_sync(3, NEPI * 32);
                 cur_l = l;
             }
-            const bool live = (t0 + row) < len_out[b];          // rows t >= len are stored as zeros (every segment layer masks its tail)
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
+            const int len = len_out[b];
+            // rows t >= len are stored as zeros (every segment layer masks its tail); rows >= T are not stored
+            float* orow = out_base + (size_t)b * out_bstride + (size_t)(t0 + q * 32 + r0) * Cout + half * 128 + c2;
+            const int trow = t0 + q * 32 + r0;
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + half * 128);
+            // step s -> (row half rh, 32-column block blk): TMEM address offset and global column offset
+            auto step_taddr = [&](int s) { const int rh = s / nblk, blk = s - rh * nblk;
+                                           return tbase + ((uint32_t)(rh * 16) << 16) + (uint32_t)((blk >> 2) * 256 + (blk & 3) * 32); };
+            auto finish = [&](const uint32_t (&rg)[16], int s) {
+                const int rh = s / nblk, blk = s - rh * nblk;
+                const int col = (blk >> 2) * 256 + (blk & 3) * 32;         // relative to this half's first column
+                const int ta = trow + rh * 16, tb = ta + 8;
+                const bool live_a = ta < len, live_b = tb < len;
+                const bool ok_a = !dup && ta < p.T_out, ok_b = !dup && tb < p.T_out;
+                float* oa = orow + (size_t)(rh * 16) * Cout + col;
+                float* ob = oa + (size_t)8 * Cout;
+                const float2* sh2 = reinterpret_cast<const float2*>(ep_shift + half * 128 + col + c2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 sh = sh2[4 * j];
+                    float2 va, vb;
+                    va.x = fmaf(__uint_as_float(rg[4 * j + 0]), wsc, sh.x);
+                    va.y = fmaf(__uint_as_float(rg[4 * j + 1]), wsc, sh.y);
+                    vb.x = fmaf(__uint_as_float(rg[4 * j + 2]), wsc, sh.x);
+                    vb.y = fmaf(__uint_as_float(rg[4 * j + 3]), wsc, sh.y);
+                    if (relu) { va.x = fmaxf(va.x, 0.f); va.y = fmaxf(va.y, 0.f); vb.x = fmaxf(vb.x, 0.f); vb.y = fmaxf(vb.y, 0.f); }
+                    if (!live_a) va = make_float2(0.f, 0.f);
+                    if (!live_b) vb = make_float2(0.f, 0.f);
+                    if (ok_a) *reinterpret_cast<float2*>(oa + 8 * j) = va;
+                    if (ok_b) *reinterpret_cast<float2*>(ob + 8 * j) = vb;
+                }
+            };
             PROF_BEGIN();
             mbar_wait(acc_full + ab, accph);
             PROF_ADD(0);
             tcgen05_fence_after();
             const int ab_cur = ab;
             if (++ab == nbuf) { ab = 0; accph ^= 1; }
-            uint32_t ra[16];
+            uint32_t ra[16], rb[16];
+            tmem_ld_16x256b_x4(step_taddr(0), ra);
+            tmem_ld_wait();
 #pragma unroll 1
-            for (int s = 0; s < nsub; ++s) {
-                const int col0 = (s >> 3) * 256 + half * 128 + (s & 7) * EPI_SUB_COLS;
-                tmem_ld_32x32b_x16(tbase + (uint32_t)col0, ra);
-                // the sub-slice's BN shift (shared-memory broadcast) is fetched while the TMEM load is in flight
-                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
-                float4 shv[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) shv[i] = sh4[i];
+            for (int s = 0; s < nstep; s += 2) {               // nstep is even
+                tmem_ld_16x256b_x4(step_taddr(s + 1), rb);
+                finish(ra, s);
                 tmem_ld_wait();
-                if (s + 1 == nsub) {                           // every TMEM read of this tile has completed
+                if (s + 2 < nstep) tmem_ld_16x256b_x4(step_taddr(s + 2), ra);
+                else {                                         // every TMEM read of this tile has completed
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * (uint32_t)ab_cur);
                 }
-                unsigned char* buf = stage + (s & 1) * EPI_SUB_BYTES;
-                if (issuer) bulk_wait_read1();                 // the store issued two sub-slices ago has left this buffer
-                named_bar_sync(1 + half, 128);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 v;
-                    v.x = fmaf(__uint_as_float(ra[4 * i + 0]), wsc, shv[i].x);
-                    v.y = fmaf(__uint_as_float(ra[4 * i + 1]), wsc, shv[i].y);
-                    v.z = fmaf(__uint_as_float(ra[4 * i + 2]), wsc, shv[i].z);
-                    v.w = fmaf(__uint_as_float(ra[4 * i + 3]), wsc, shv[i].w);
-                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(buf + row_off + (((uint32_t)i ^ row_sw) << 4)) = v;   // SWIZZLE_64B
-                }
-                fence_proxy_async();
-                named_bar_sync(1 + half, 128);
-                if (issuer && !dup) { tma_store_3d(&L->tm_out, buf, col0, t0, b); bulk_commit(); }
+                finish(rb, s + 1);
+                tmem_ld_wait();
             }
-            if (issuer && !dup) {
-                // this half's part of the tile is in global memory: publish it to the tiles of the next layer
-                bulk_wait_all0();
-                fence_proxy_async_all();
+            if (!dup) {
+                // this warp's part of the tile is in global memory: publish it to the tiles of the next layer
                 __threadfence();
-                atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
+                __syncwarp();
+                if (lane == 0) atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
             }
             PROF_ADD(1);
         }
-        if (issuer) bulk_wait_all0();
     }
     } else {
         // ======== depthwise producers, two groups on alternate chunks ========
@@ -1579,16 +1611,13 @@ static int encode_act(CUtensorMap* tm, const float* base, int B, int T, int C, l
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
     return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
-// output [B, T, C] fp32 -> 3-D map (C, T, B), box (cols, rows, 1); 32 columns: SWIZZLE_128B, 16 columns: SWIZZLE_64B
-// (rows beyond T are clipped by the TMA)
-static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride, int box_rows = TN,
-                      int box_cols = 32)
+// output [B, T, C] fp32 -> 3-D map (C, T, B), box (32, rows, 1), SWIZZLE_128B (rows beyond T are clipped by the TMA)
+static int encode_out(CUtensorMap* tm, const float* base, int B, int T, int C, long long bstride, int box_rows = TN)
 {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)bstride * 4};
-    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box,
-                     box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    return encode_tm(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 // weights [Cout, Cin] fp16 -> 2-D map (Cin, Cout), box (32, 256), SWIZZLE_64B
 static int encode_w(CUtensorMap* tm, const __half* base, int Cout, int Cin, int box_rows = 256)
@@ -1656,7 +1685,7 @@ static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int*
 static bool pick_rings_pair(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots)
 {
     const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart;
-    const int overhead = SMEM_FIXED + 4 * EPI_SUB_BYTES;
+    const int overhead = SMEM_FIXED;                        // the pair kernel's epilogue stores from registers: no staging
     int xs = 3, bs = 3;
     int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
     if (slots < nN) { bs = 2; slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot; }
@@ -1940,13 +1969,13 @@ static bool plan_segment(const SegLayer* L, int n, int npart, int T, int nb, Seg
         if (const char* e = getenv("VASR_TC_RINGS")) {
             int xs = 0, bs = 0, as = 0;
             if (sscanf(e, "%d,%d,%d", &xs, &bs, &as) == 3 && xs >= 2 && xs <= MAX_STAGES && bs >= 2 && bs <= MAX_STAGES && as >= nN && as <= 16 &&
-                (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED + 4 * EPI_SUB_BYTES <= (size_t)SMEM_LIMIT) {
+                (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED <= (size_t)SMEM_LIMIT) {
                 pl->xstages = xs; pl->bstages = bs; pl->aslots = as;
             }
         }
 #endif
         pl->smem = (size_t)pl->aslots * W_HALF * npart + (size_t)pl->bstages * PART_BYTES * npart +
-                   (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED + 4 * EPI_SUB_BYTES;
+                   (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED;
         return true;
     }
     pick_rings(npart, pl->x_stage_bytes, nN, 2 * EPI_STAGE_BYTES, &pl->xstages, &pl->bstages, &pl->aslots);
@@ -2009,13 +2038,14 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
                     if ((rc = encode_w(&d.tm_r_hi, (const __half*)sb.res_h, sb.cout, sb.res_cin, 128))) return rc;
                     if ((rc = encode_w(&d.tm_r_lo, (const __half*)sb.res_l, sb.cout, sb.res_cin, 128))) return rc;
                 } else { d.tm_r_hi = d.tm_w_hi; d.tm_r_lo = d.tm_w_lo; }
-                if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, TN, EPI_SUB_COLS))) return rc;
+                d.tm_out = d.tm_x;                            // unused: the pair kernel stores from registers
             } else {
                 memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
                 memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
                 if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, tr))) return rc;
             }
             d.dw_w = sb.dw_tc; d.shift = sb.shift; d.len_out = L[i].len_out; d.wscale_inv = sb.wscale_inv_scalar;
+            d.out = L[i].y; d.out_bstride = L[i].ys;
             d.K = sb.kernel; d.n_main = sb.cin / KC; d.n_res = sb.has_res ? sb.res_cin / KC : 0;
             d.relu = sb.relu ? 1 : 0; d.mask_tail = 1; d.pad = sb.pad;
         }
