@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <vector>
+#include <type_traits>
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -1139,8 +1140,9 @@ segment_kernel(const SegParams p)
 // prefetch.
 //
 // Depthwise: 8 warps in two groups (warps 0-3 / 4-7) that take alternate chunks, i.e. two depthwise warps per SM
-// sub-partition whose FMA streams fill each other's stalls and fp16-split/store phases.  The kernel starts at 96
-// registers per thread and re-partitions with setmaxnreg: 128 for the two depthwise warpgroups, 72 for the rest.
+// sub-partition whose FMA streams fill each other's stalls and fp16-split/store phases.  512 threads, so every
+// thread may use 128 registers (no setmaxnreg re-partitioning needed): warps 0-7 depthwise, 8 window producer,
+// 9 weight producer, 10 MMA issuer, 11 idle, 12-15 epilogue (one per TMEM lane quarter).
 //
 // Work list: static.  Item i = (layer, pair of tiles); cluster c executes items c, c + n_clusters, ... in increasing
 // order.  An item only depends on items with a smaller index (previous layer, same utterance), and every cluster works
@@ -1202,22 +1204,14 @@ __device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar)          // ar
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-// 16 lanes x 256 bit, x4: rows (lane/4, lane/4 + 8) x columns 8j + 2(lane%4) + {0,1}, j = 0..3 -> r[4j + {0,1}] (row lane/4),
-// r[4j + {2,3}] (row lane/4 + 8)   (cute SM100_TMEM_LOAD_16dp256b4x)
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // D = f32, A = B = f16, both K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
 constexpr uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr int W_HALF = 128 * KC * 2;            // this CTA's half of a weight block: [128 co x 64 B] fp16 = 8 KiB per part
-constexpr int PAIR_THREADS = 640;
+constexpr int PAIR_THREADS = 512;              // 8 depthwise warps, window / weight / MMA warps (+ 1 idle), 4 epilogue warps
+constexpr int NEPI_PAIR = 4;                    // one epilogue warp per TMEM lane quarter
+constexpr int EPI_WARP_BYTES = 32 * 32 * 4;     // one 32-row x 32-channel fp32 block (SWIZZLE_128B); two per epilogue warp
 
 template <int NPART>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
@@ -1232,7 +1226,8 @@ segment_pair_kernel(const SegParams p)
     unsigned char* a_ring = smem;
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
     unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + (size_t)p.xstages * p.x_stage_bytes);
+    unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;      // [4 warps][2][32 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + NEPI_PAIR * 2 * EPI_WARP_BYTES);
     const int XSTAGES = p.xstages, BSTAGES = p.bstages;
     uint64_t* full_x = bars;
     uint64_t* empty_x = full_x + MAX_STAGES;
@@ -1260,7 +1255,7 @@ segment_pair_kernel(const SegParams p)
         for (int i = 0; i < XSTAGES; ++i) { mbar_init(full_x + i, 1); mbar_init(empty_x + i, GW); }
         for (int i = 0; i < BSTAGES; ++i) { mbar_init(full_b + i, 2 * GW); mbar_init(empty_b + i, 1); }
         for (int i = 0; i < p.aslots; ++i) { mbar_init(full_a + i, 1); mbar_init(empty_a + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * NEPI); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 2 * NEPI_PAIR); }
         fence_barrier_init();
     }
     if (warp == WARP_MMA) {                                // one warp of each CTA, same warp id in both
@@ -1284,7 +1279,6 @@ segment_pair_kernel(const SegParams p)
     };
 
     if (warp >= NDW_PAIR) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == WARP_X) {
         // ======== TMA producer of this CTA's activation windows (+ cross-layer dependency wait) ========
         if (lane == 0) {
@@ -1294,9 +1288,9 @@ segment_pair_kernel(const SegParams p)
                 decode(item, l, b, t0, dup);
                 const LayerDesc* L = p.layers + l;
                 if (l > 0) {
-                    // every tile of layer l-1 of this utterance has been stored (all eight epilogue warps of each time tile)
+                    // every tile of layer l-1 of this utterance has been stored (all four epilogue warps of each time tile)
                     const int* flag = p.done + (size_t)(l - 1) * p.done_stride + b;
-                    const int need = NEPI * p.n_tt;
+                    const int need = NEPI_PAIR * p.n_tt;
                     PROF_BEGIN();
                     dep_wait(flag, need);
                     PROF_ADD(1);
@@ -1376,6 +1370,7 @@ segment_pair_kernel(const SegParams p)
                         for (int ks = 0; ks < KC / 16; ++ks) {
                             const uint64_t x_hi = make_desc_sw64(b_addr + ks * 32);
                             const uint64_t w_hi = make_desc_sw64(w_addr + ks * 32);
+                            if (DBG_ON(1)) continue;
                             umma_f16_2sm(d, x_hi, w_hi, IDESC_F16_M256_N256, (c > 0 || ks > 0) ? 1u : 0u);
                             if (NPART == 2) {
                                 const uint64_t x_lo = make_desc_sw64(b_addr + PART_BYTES + ks * 32);
@@ -1396,104 +1391,97 @@ segment_pair_kernel(const SegParams p)
             }
         }
     } else if (warp >= WARP_EPI) {
-        // ======== epilogue of this CTA's 128 rows: TMEM -> +shift, ReLU, mask -> global memory, no staging ========
-        // tcgen05.ld.16x256b hands a warp the accumulator in the classic 16 x 8 fragment layout: thread t holds rows
-        // t/4 and t/4 + 8, columns 2(t%4), 2(t%4)+1 of every 8-column block.  A warp-wide 8-byte store therefore
-        // writes eight full 32-byte sectors (8 rows x 8 channels): sector-exact global writes straight from
-        // registers - no shared-memory staging, no TMA store, no barriers between the epilogue warps.  Each warp drains
-        // its 32 rows x 256 columns (its half of every N block) in 16 loads of 16 registers, software-pipelined so
-        // that the next TMEM load is in flight while the current fragment is finished and stored.
+        // ======== epilogue of this CTA's 128 rows: TMEM -> +shift, ReLU, mask -> per-warp smem staging -> TMA store ========
+        // One warp per TMEM lane quarter; TMEM lane = time row, so a thread owns one output row.  Per 32-column block:
+        // tcgen05.ld.32x32b.x32 -> registers -> 128-byte SWIZZLE_128B rows in a 4 KiB buffer PRIVATE to the warp -> one
+        // TMA store (32 rows x 32 channels, full 128-byte lines; rows beyond T are clipped by the tensor map).  Two
+        // buffers per warp and the next block's TMEM load issued before the current block is finished, so the only
+        // synchronisation is inside the warp: no block-wide barrier sits between TMEM and the store.  (Measured:
+        // block-wide staging with named barriers drained a 128 x 512 tile in 18 k cycles, register-direct 8-byte stores
+        // in 17 k - the LSU pays per 128-byte line touched; the TMA store itself costs < 2 k.)  The accumulator is
+        // single-buffered for 512 channels, so the drain time is what the MMA issuer waits for at every tile.
         const int q = warp & 3;
-        const int half = (warp - WARP_EPI) >> 2;
-        const int r0 = lane >> 2;                              // row within a 16-row block (this thread also owns r0 + 8)
-        const int c2 = (lane & 3) * 2;                         // column pair within an 8-column block
+        const int row = q * 32 + lane;                         // tile row (time) owned by this thread
+        unsigned char* stage = epi_stage + (size_t)q * 2 * EPI_WARP_BYTES;
         const uint32_t acc_empty_leader = mapa_u32(acc_empty, 0);
-        const int nblk = p.nN * 4;                             // 32-column blocks of this half-group per tile
-        const int nstep = 2 * nblk;                            // x two 16-row halves of the warp's lane quarter
-        const int Cout = p.nN * 256;
+        const int nblk = p.nN * 8;                             // 32-column blocks per tile
+        const uint32_t row_off = (uint32_t)lane * 128u, row_sw = (uint32_t)lane & 7u;
         int cur_l = -1;
-        float wsc = 1.f; int relu = 0; const int* len_out = nullptr;
-        float* out_base = nullptr; long long out_bstride = 0;
+        float2 wsc2 = make_float2(1.f, 1.f); const int* len_out = nullptr;
         int ab = 0; uint32_t accph = 0;
+        uint32_t nstore = 0;                                   // blocks staged so far (buffer parity)
         for (int item = item0; item < n_items; item += item_step) {
             int l, b, t0; bool dup;
             decode(item, l, b, t0, dup);
             const LayerDesc* L = p.layers + l;
             if (l != cur_l) {                                  // per-channel BN shift + scalars of the new layer
-                named_bar_sync(3, NEPI * 32);
+                named_bar_sync(3, NEPI_PAIR * 32);
                 const float* shift = L->shift;
-                for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI * 32) ep_shift[i] = __ldg(shift + i);
-                wsc = L->wscale_inv; relu = L->relu; len_out = L->len_out; out_base = L->out; out_bstride = L->out_bstride;
-                named_bar_sync(3, NEPI * 32);
+                for (int i = (warp - WARP_EPI) * 32 + lane; i < p.nN * 256; i += NEPI_PAIR * 32) ep_shift[i] = __ldg(shift + i);
+                wsc2 = make_float2(L->wscale_inv, L->wscale_inv); len_out = L->len_out;
+                named_bar_sync(3, NEPI_PAIR * 32);
                 cur_l = l;
             }
-            const int len = len_out[b];
-            // rows t >= len are stored as zeros (every segment layer masks its tail); rows >= T are not stored
-            float* orow = out_base + (size_t)b * out_bstride + (size_t)(t0 + q * 32 + r0) * Cout + half * 128 + c2;
-            const int trow = t0 + q * 32 + r0;
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols + half * 128);
-            // step s -> (row half rh, 32-column block blk): TMEM address offset and global column offset
-            auto step_taddr = [&](int s) { const int rh = s / nblk, blk = s - rh * nblk;
-                                           return tbase + ((uint32_t)(rh * 16) << 16) + (uint32_t)((blk >> 2) * 256 + (blk & 3) * 32); };
-            auto finish = [&](const uint32_t (&rg)[16], int s) {
-                const int rh = s / nblk, blk = s - rh * nblk;
-                const int col = (blk >> 2) * 256 + (blk & 3) * 32;         // relative to this half's first column
-                const int ta = trow + rh * 16, tb = ta + 8;
-                const bool live_a = ta < len, live_b = tb < len;
-                const bool ok_a = !dup && ta < p.T_out, ok_b = !dup && tb < p.T_out;
-                float* oa = orow + (size_t)(rh * 16) * Cout + col;
-                float* ob = oa + (size_t)8 * Cout;
-                const float2* sh2 = reinterpret_cast<const float2*>(ep_shift + half * 128 + col + c2);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 sh = sh2[4 * j];
-                    float2 va, vb;
-                    va.x = fmaf(__uint_as_float(rg[4 * j + 0]), wsc, sh.x);
-                    va.y = fmaf(__uint_as_float(rg[4 * j + 1]), wsc, sh.y);
-                    vb.x = fmaf(__uint_as_float(rg[4 * j + 2]), wsc, sh.x);
-                    vb.y = fmaf(__uint_as_float(rg[4 * j + 3]), wsc, sh.y);
-                    if (relu) { va.x = fmaxf(va.x, 0.f); va.y = fmaxf(va.y, 0.f); vb.x = fmaxf(vb.x, 0.f); vb.y = fmaxf(vb.y, 0.f); }
-                    if (!live_a) va = make_float2(0.f, 0.f);
-                    if (!live_b) vb = make_float2(0.f, 0.f);
-                    if (ok_a) *reinterpret_cast<float2*>(oa + 8 * j) = va;
-                    if (ok_b) *reinterpret_cast<float2*>(ob + 8 * j) = vb;
-                }
-            };
+            // rows t >= len are stored as zeros (every segment layer masks its tail)
+            const bool live = (t0 + row) < len_out[b];
+            const bool masked = __any_sync(0xffffffffu, !live);          // warp-uniform
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
             PROF_BEGIN();
             mbar_wait(acc_full + ab, accph);
             PROF_ADD(0);
             tcgen05_fence_after();
             const int ab_cur = ab;
             if (++ab == nbuf) { ab = 0; accph ^= 1; }
-            uint32_t ra[16], rb[16];
-            tmem_ld_16x256b_x4(step_taddr(0), ra);
+            // finish one 32-column block held in registers: +shift, ReLU, (mask), stage, TMA store
+            auto finish = [&](const uint32_t (&rg)[32], int col0) {
+                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                unsigned char* buf = stage + (nstore & 1u) * EPI_WARP_BYTES;
+                if (lane == 0) bulk_wait_read1();              // the store issued two blocks ago has left this buffer
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 sh = sh4[i];
+                    float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 0]), __uint_as_float(rg[4 * i + 1])), wsc2, make_float2(sh.x, sh.y));
+                    float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 2]), __uint_as_float(rg[4 * i + 3])), wsc2, make_float2(sh.z, sh.w));
+                    float4 v = make_float4(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f), fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f));
+                    if (masked && !live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(buf + row_off + (((uint32_t)i ^ row_sw) << 4)) = v;   // SWIZZLE_128B
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !dup) { tma_store_3d(&L->tm_out, buf, col0, t0 + q * 32, b); bulk_commit(); }
+                ++nstore;
+            };
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32b_x32(tbase, ra);
             tmem_ld_wait();
 #pragma unroll 1
-            for (int s = 0; s < nstep; s += 2) {               // nstep is even
-                tmem_ld_16x256b_x4(step_taddr(s + 1), rb);
-                finish(ra, s);
+            for (int blk = 0; blk < nblk; blk += 2) {          // nblk is even
+                tmem_ld_32x32b_x32(tbase + (uint32_t)((blk + 1) * 32), rb);
+                finish(ra, blk * 32);
                 tmem_ld_wait();
-                if (s + 2 < nstep) tmem_ld_16x256b_x4(step_taddr(s + 2), ra);
+                if (blk + 2 < nblk) tmem_ld_32x32b_x32(tbase + (uint32_t)((blk + 2) * 32), ra);
                 else {                                         // every TMEM read of this tile has completed
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * (uint32_t)ab_cur);
                 }
-                finish(rb, s + 1);
+                finish(rb, (blk + 1) * 32);
                 tmem_ld_wait();
             }
-            if (!dup) {
+            if (lane == 0 && !dup) {
                 // this warp's part of the tile is in global memory: publish it to the tiles of the next layer
+                bulk_wait_all0();
+                fence_proxy_async_all();
                 __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
+                atomicAdd(p.done + (size_t)l * p.done_stride + b, 1);
             }
             PROF_ADD(1);
         }
+        if (lane == 0) bulk_wait_all0();
     }
     } else {
         // ======== depthwise producers, two groups on alternate chunks ========
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         constexpr int R = TN / (2 * GW);
         constexpr int XP = KC / 2;
         const int grp = warp >> 2;
@@ -1521,7 +1509,7 @@ segment_pair_kernel(const SegParams p)
                 PROF_ADD(0);
                 const float2* xs = reinterpret_cast<const float2*>(x_ring + (size_t)sx * p.x_stage_bytes) + cp;
                 float2 acc[R];
-                if (c < n_main) {
+                if (c < n_main && !DBG_ON(2)) {
                     const float2* wp = tap_base(x_ring + (size_t)sx * p.x_stage_bytes + x_w_off, cp);
                     SEG_K_SWITCH(K, (dw_chunk_s1<KK, 1, R>(xs, wp, tw, acc)));
                 } else {
@@ -1685,7 +1673,7 @@ static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int*
 static bool pick_rings_pair(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots)
 {
     const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart;
-    const int overhead = SMEM_FIXED;                        // the pair kernel's epilogue stores from registers: no staging
+    const int overhead = SMEM_FIXED + NEPI_PAIR * 2 * EPI_WARP_BYTES;   // + the epilogue warps' private staging buffers
     int xs = 3, bs = 3;
     int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
     if (slots < nN) { bs = 2; slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot; }
@@ -1969,13 +1957,13 @@ static bool plan_segment(const SegLayer* L, int n, int npart, int T, int nb, Seg
         if (const char* e = getenv("VASR_TC_RINGS")) {
             int xs = 0, bs = 0, as = 0;
             if (sscanf(e, "%d,%d,%d", &xs, &bs, &as) == 3 && xs >= 2 && xs <= MAX_STAGES && bs >= 2 && bs <= MAX_STAGES && as >= nN && as <= 16 &&
-                (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED <= (size_t)SMEM_LIMIT) {
+                (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED + NEPI_PAIR * 2 * EPI_WARP_BYTES <= (size_t)SMEM_LIMIT) {
                 pl->xstages = xs; pl->bstages = bs; pl->aslots = as;
             }
         }
 #endif
         pl->smem = (size_t)pl->aslots * W_HALF * npart + (size_t)pl->bstages * PART_BYTES * npart +
-                   (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED;
+                   (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED + NEPI_PAIR * 2 * EPI_WARP_BYTES;
         return true;
     }
     pick_rings(npart, pl->x_stage_bytes, nN, 2 * EPI_STAGE_BYTES, &pl->xstages, &pl->bstages, &pl->aslots);
@@ -2038,7 +2026,7 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
                     if ((rc = encode_w(&d.tm_r_hi, (const __half*)sb.res_h, sb.cout, sb.res_cin, 128))) return rc;
                     if ((rc = encode_w(&d.tm_r_lo, (const __half*)sb.res_l, sb.cout, sb.res_cin, 128))) return rc;
                 } else { d.tm_r_hi = d.tm_w_hi; d.tm_r_lo = d.tm_w_lo; }
-                d.tm_out = d.tm_x;                            // unused: the pair kernel stores from registers
+                if ((rc = encode_out(&d.tm_out, L[i].y, B, T, sb.cout, L[i].ys, 32))) return rc;   // per-warp 32-row stores
             } else {
                 memcpy(&d.tm_w_hi, sb.tm_w_hi, sizeof(CUtensorMap)); memcpy(&d.tm_w_lo, sb.tm_w_lo, sizeof(CUtensorMap));
                 memcpy(&d.tm_r_hi, sb.tm_r_hi, sizeof(CUtensorMap)); memcpy(&d.tm_r_lo, sb.tm_r_lo, sizeof(CUtensorMap));
@@ -2048,6 +2036,7 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
             d.out = L[i].y; d.out_bstride = L[i].ys;
             d.K = sb.kernel; d.n_main = sb.cin / KC; d.n_res = sb.has_res ? sb.res_cin / KC : 0;
             d.relu = sb.relu ? 1 : 0; d.mask_tail = 1; d.pad = sb.pad;
+            if (pair && !sb.relu) return set_error(VASR_EINVAL, "tcgen05 path: the pair kernel's epilogue applies ReLU unconditionally");
         }
         if (g_seg_cache.size() >= 64) {                      // bounded: drop everything once nothing can still be reading it
             VASR_CUDA_OK(cudaDeviceSynchronize());
