@@ -35,7 +35,7 @@ constexpr int KC = 32;                  // input channels per chunk
 constexpr int NDW = 4;                  // depthwise warps of the single-CTA kernels: thread = channel pair x 16 outputs
 constexpr int NEPI = 8;                 // epilogue warps: any 8 consecutive warps cover each TMEM lane quarter (warp & 3) twice
 constexpr int NTHREADS = (NDW + 3 + NEPI) * 32;            // 480: 4 depthwise, window / weight / MMA warps, 8 epilogue
-constexpr int MAX_STAGES = 4;           // upper bound of the activation-window / B-operand ring depths
+constexpr int MAX_STAGES = 8;           // upper bound of the activation-window / operand ring depths
 constexpr int SCHED = 4;                // depth of the tile ring
 constexpr int SCHED_CONSUMERS = 1 /*weights*/ + 1 /*MMA*/ + NDW + NEPI;
 constexpr int PART_BYTES = 128 * KC * 2;   // activation operand: [128 t rows x 64 B] fp16 = 8 KiB per part
@@ -1449,7 +1449,7 @@ segment_pair_kernel(const SegParams p)
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0 && !dup) { tma_store_3d(&L->tm_out, buf, col0, t0 + q * 32, b); bulk_commit(); }
+                if (lane == 0 && !dup && !DBG_ON(4)) { tma_store_3d(&L->tm_out, buf, col0, t0 + q * 32, b); bulk_commit(); }
                 ++nstore;
             };
             uint32_t ra[32], rb[32];
