@@ -2,7 +2,7 @@
 """Run the 15x5 encoder under several environment settings (one subprocess each, the library reads its switches
 once) on the same seeded input and compare every variant's output with the first one.
 
-Usage: python tools/cmp_variants.py B seconds "NAME=ENV1=a,ENV2=b" "NAME2=..."      (first variant = reference)
+Usage: python tools/cmp_variants.py B seconds "NAME=ENV1=a;ENV2=b" "NAME2=..."      (first variant = reference)
 Prints per variant: encoder ms per pass (back to back), max |diff| and rel-L2 vs the reference variant."""
 import os
 import subprocess
@@ -52,7 +52,7 @@ if __name__ == "__main__":
     for spec in sys.argv[3:]:
         name, _, envs = spec.partition("=")
         env = dict(os.environ)
-        for kv in filter(None, envs.split(",")):
+        for kv in filter(None, envs.split(";")):
             k, _, v = kv.partition("=")
             env[k] = v
         out = f"/tmp/cmp_{name}.pt"
@@ -68,7 +68,7 @@ if __name__ == "__main__":
             txt = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
             rc = "TIMEOUT"
         for line in txt.splitlines():
-            if "encoder ms" in line or "TCSEG" in line or "TCPROF" in line or "rror" in line:
+            if "encoder ms" in line or "TCSEG" in line or "TCPROF" in line or "rror" in line or "ignored" in line:
                 print("  " + line.strip())
         print(f"  rc={rc}", flush=True)
         if not os.path.exists(out):

@@ -719,6 +719,7 @@ struct SegParams {
     int done_stride;
     int T_out, nN;
     int x_stage_bytes, xstages, bstages, aslots;
+    int epi_bufs;            // pair kernel: 4 KiB store-staging buffers per epilogue warp (2..4)
     int b0, n_tt, n_utt;
     unsigned long long* prof;
     int dbg;
@@ -1204,7 +1205,7 @@ __device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar)          // ar
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // D = f32, A = B = f16, both K-major, N = 256, M = 256 (128 rows in each CTA of the pair)
 constexpr uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
@@ -1227,7 +1228,7 @@ segment_pair_kernel(const SegParams p)
     unsigned char* b_ring = a_ring + (size_t)p.aslots * A_SLOT;
     unsigned char* x_ring = b_ring + (size_t)p.bstages * B_STAGE;
     unsigned char* epi_stage = x_ring + (size_t)p.xstages * p.x_stage_bytes;      // [4 warps][2][32 rows x 128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + NEPI_PAIR * 2 * EPI_WARP_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (size_t)NEPI_PAIR * p.epi_bufs * EPI_WARP_BYTES);
     const int XSTAGES = p.xstages, BSTAGES = p.bstages;
     uint64_t* full_x = bars;
     uint64_t* empty_x = full_x + MAX_STAGES;
@@ -1304,7 +1305,9 @@ segment_pair_kernel(const SegParams p)
                     mbar_wait(empty_x + s, xph ^ 1);
                     PROF_ADD(0);
                     unsigned char* dst = x_ring + (size_t)s * p.x_stage_bytes;
-                    if (c < n_main) {
+                    if (DBG_ON(16)) {                                  // ablation: no window traffic (stale windows)
+                        mbar_arrive(full_x + s);
+                    } else if (c < n_main) {
                         mbar_arrive_expect_tx(full_x + s, (uint32_t)(n_xbox * xbox_rows * KC * 4 + tap_floats(K) * 4));
                         for (int j = 0; j < n_xbox; ++j)
                             tma_load_3d(dst + (size_t)j * xbox_rows * KC * 4, &L->tm_x, c * KC, t0 - pad + j * xbox_rows, b, full_x + s);
@@ -1332,6 +1335,11 @@ segment_pair_kernel(const SegParams p)
                         mbar_wait(empty_a + slot, ph ^ 1);                    // released in both CTAs by the multicast commit
                         PROF_ADD(0);
                         // all bytes of the slot (both halves) are accounted on the leader's barrier
+                        if (DBG_ON(8)) {                               // ablation: no weight traffic (stale operands)
+                            if (leader) mbar_arrive(full_a + slot);
+                            if (++slot == p.aslots) { slot = 0; ph ^= 1; }
+                            continue;
+                        }
                         if (leader) mbar_arrive_expect_tx(full_a + slot, (uint32_t)(2 * A_SLOT));
                         unsigned char* dst = a_ring + (size_t)slot * A_SLOT;
                         const int co = m * 256 + (int)rank * 128;
@@ -1402,14 +1410,15 @@ segment_pair_kernel(const SegParams p)
         // single-buffered for 512 channels, so the drain time is what the MMA issuer waits for at every tile.
         const int q = warp & 3;
         const int row = q * 32 + lane;                         // tile row (time) owned by this thread
-        unsigned char* stage = epi_stage + (size_t)q * 2 * EPI_WARP_BYTES;
+        unsigned char* stage = epi_stage + (size_t)q * p.epi_bufs * EPI_WARP_BYTES;
+        const uint32_t nbufs = (uint32_t)p.epi_bufs;
         const uint32_t acc_empty_leader = mapa_u32(acc_empty, 0);
         const int nblk = p.nN * 8;                             // 32-column blocks per tile
         const uint32_t row_off = (uint32_t)lane * 128u, row_sw = (uint32_t)lane & 7u;
         int cur_l = -1;
         float2 wsc2 = make_float2(1.f, 1.f); const int* len_out = nullptr;
         int ab = 0; uint32_t accph = 0;
-        uint32_t nstore = 0;                                   // blocks staged so far (buffer parity)
+        uint32_t sbuf = 0;                                     // staging buffer of the next block (round robin)
         for (int item = item0; item < n_items; item += item_step) {
             int l, b, t0; bool dup;
             decode(item, l, b, t0, dup);
@@ -1435,8 +1444,9 @@ segment_pair_kernel(const SegParams p)
             // finish one 32-column block held in registers: +shift, ReLU, (mask), stage, TMA store
             auto finish = [&](const uint32_t (&rg)[32], int col0) {
                 const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
-                unsigned char* buf = stage + (nstore & 1u) * EPI_WARP_BYTES;
-                if (lane == 0) bulk_wait_read1();              // the store issued two blocks ago has left this buffer
+                unsigned char* buf = stage + sbuf * EPI_WARP_BYTES;
+                // the store issued `nbufs` blocks ago has left this buffer
+                if (lane == 0) { if (nbufs == 2) bulk_wait_read<1>(); else if (nbufs == 3) bulk_wait_read<2>(); else bulk_wait_read<3>(); }
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -1450,7 +1460,7 @@ segment_pair_kernel(const SegParams p)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && !dup && !DBG_ON(4)) { tma_store_3d(&L->tm_out, buf, col0, t0 + q * 32, b); bulk_commit(); }
-                ++nstore;
+                if (++sbuf == nbufs) sbuf = 0;
             };
             uint32_t ra[32], rb[32];
             tmem_ld_32x32b_x32(tbase, ra);
@@ -1670,17 +1680,18 @@ static void pick_rings(int npart, int x_stage_bytes, int nN, int epi_bytes, int*
 // ring depths of the pair kernel: each depthwise group holds a window stage while it computes, so a third stage is what
 // lets the loads run ahead (with two, every chunk exposes its TMA latency); three operand stages let the depthwise
 // warps work through the accumulator drain at the end of a tile; the rest goes to 16 KiB (half-block) weight slots.
-static bool pick_rings_pair(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots)
+static bool pick_rings_pair(int npart, int x_stage_bytes, int nN, int* xstages, int* bstages, int* aslots, int* epi_bufs)
 {
-    const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart;
-    const int overhead = SMEM_FIXED + NEPI_PAIR * 2 * EPI_WARP_BYTES;   // + the epilogue warps' private staging buffers
-    int xs = 3, bs = 3;
-    int slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot;
-    if (slots < nN) { bs = 2; slots = (SMEM_LIMIT - overhead - bs * b_stage - xs * x_stage_bytes) / w_slot; }
+    const int w_slot = W_HALF * npart, b_stage = PART_BYTES * npart, e_buf = NEPI_PAIR * EPI_WARP_BYTES;
+    int xs = 3, bs = 3, eb = 2;
+    int slots = (SMEM_LIMIT - SMEM_FIXED - eb * e_buf - bs * b_stage - xs * x_stage_bytes) / w_slot;
+    if (slots < nN) { bs = 2; slots = (SMEM_LIMIT - SMEM_FIXED - eb * e_buf - bs * b_stage - xs * x_stage_bytes) / w_slot; }
     if (slots < nN) return false;
-    if (slots > 4 * nN) slots = 4 * nN;
-    if (slots > 16) slots = 16;
-    *xstages = xs; *bstages = bs; *aslots = slots;
+    if (slots > nN + 1) slots = nN + 1;                     // one chunk of weights + one slot of prefetch; then staging
+    int left = SMEM_LIMIT - SMEM_FIXED - eb * e_buf - bs * b_stage - xs * x_stage_bytes - slots * w_slot;
+    while (eb < 4 && left >= e_buf) { ++eb; left -= e_buf; }
+    while (slots < 4 * nN && slots < 16 && left >= w_slot) { ++slots; left -= w_slot; }
+    *xstages = xs; *bstages = bs; *aslots = slots; *epi_bufs = eb;
     return true;
 }
 
@@ -1928,7 +1939,7 @@ bool segment_tc_layer_ok(const SubBlock& sb)
 struct SegPlan {
     int tr;                  // valid rows per tile: 128, or 32 (latency mode)
     bool pair;               // CTA-pair kernel (cta_group::2)
-    int x_stage_bytes, xstages, bstages, aslots;
+    int x_stage_bytes, xstages, bstages, aslots, epi_bufs;
     size_t smem;
 };
 static int seg_x_stage_bytes(const SegLayer* L, int n, int tr)
@@ -1951,19 +1962,22 @@ static bool plan_segment(const SegLayer* L, int n, int npart, int T, int nb, Seg
     pl->pair = false;
     pl->x_stage_bytes = seg_x_stage_bytes(L, n, pl->tr);
     if (!lat && dev_env("VASR_TC_PAIR", 1) != 0 && g_num_sms >= 2 &&
-        pick_rings_pair(npart, pl->x_stage_bytes, nN, &pl->xstages, &pl->bstages, &pl->aslots)) {
+        pick_rings_pair(npart, pl->x_stage_bytes, nN, &pl->xstages, &pl->bstages, &pl->aslots, &pl->epi_bufs)) {
         pl->pair = true;
+        auto pair_smem = [&](int xs, int bs, int as, int eb) {
+            return (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED +
+                   (size_t)eb * NEPI_PAIR * EPI_WARP_BYTES;
+        };
 #ifdef VASR_DEV
-        if (const char* e = getenv("VASR_TC_RINGS")) {
-            int xs = 0, bs = 0, as = 0;
-            if (sscanf(e, "%d,%d,%d", &xs, &bs, &as) == 3 && xs >= 2 && xs <= MAX_STAGES && bs >= 2 && bs <= MAX_STAGES && as >= nN && as <= 16 &&
-                (size_t)as * W_HALF * npart + (size_t)bs * PART_BYTES * npart + (size_t)xs * pl->x_stage_bytes + SMEM_FIXED + NEPI_PAIR * 2 * EPI_WARP_BYTES <= (size_t)SMEM_LIMIT) {
-                pl->xstages = xs; pl->bstages = bs; pl->aslots = as;
-            }
+        if (const char* e = getenv("VASR_TC_RINGS")) {         // x,b,a,e: window / operand stages, weight slots, staging buffers
+            int xs = 0, bs = 0, as = 0, eb = 0;
+            if (sscanf(e, "%d,%d,%d,%d", &xs, &bs, &as, &eb) == 4 && xs >= 2 && xs <= MAX_STAGES && bs >= 2 && bs <= MAX_STAGES && as >= nN &&
+                as <= 16 && eb >= 2 && eb <= 4 && pair_smem(xs, bs, as, eb) <= (size_t)SMEM_LIMIT) {
+                pl->xstages = xs; pl->bstages = bs; pl->aslots = as; pl->epi_bufs = eb;
+            } else fprintf(stderr, "VASR_TC_RINGS=%s does not fit this segment (x stage %d bytes): ignored\n", e, pl->x_stage_bytes);
         }
 #endif
-        pl->smem = (size_t)pl->aslots * W_HALF * npart + (size_t)pl->bstages * PART_BYTES * npart +
-                   (size_t)pl->xstages * pl->x_stage_bytes + SMEM_FIXED + NEPI_PAIR * 2 * EPI_WARP_BYTES;
+        pl->smem = pair_smem(pl->xstages, pl->bstages, pl->aslots, pl->epi_bufs);
         return true;
     }
     pick_rings(npart, pl->x_stage_bytes, nN, 2 * EPI_STAGE_BYTES, &pl->xstages, &pl->bstages, &pl->aslots);
@@ -1997,7 +2011,7 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
     const int tr = pl.tr;
     const bool pair = pl.pair;
     SegParams p{};
-    p.x_stage_bytes = pl.x_stage_bytes; p.xstages = pl.xstages; p.bstages = pl.bstages; p.aslots = pl.aslots;
+    p.x_stage_bytes = pl.x_stage_bytes; p.xstages = pl.xstages; p.bstages = pl.bstages; p.aslots = pl.aslots; p.epi_bufs = pl.epi_bufs;
     p.nN = L[0].sb->cout / 256;
     const int variant = pair ? 256 : tr;                      // key of the descriptor cache (weight / output boxes differ)
     std::vector<SegLayerKey> key((size_t)n);
@@ -2077,8 +2091,8 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
 #ifdef VASR_DEV
     if (p.prof) {
         char head[200];
-        snprintf(head, sizeof(head), "TCSEG%s layers=%d k=%d..%d cout=%d items=%lld ctas=%d tr=%d xs=%d bs=%d as=%d", pair ? "(pair)" : "", n,
-                 L[0].sb->kernel, L[n - 1].sb->kernel, L[0].sb->cout, n_items, (int)grid.x, tr, p.xstages, p.bstages, p.aslots);
+        snprintf(head, sizeof(head), "TCSEG%s layers=%d k=%d..%d cout=%d items=%lld ctas=%d tr=%d xs=%d bs=%d as=%d eb=%d", pair ? "(pair)" : "", n,
+                 L[0].sb->kernel, L[n - 1].sb->kernel, L[0].sb->cout, n_items, (int)grid.x, tr, p.xstages, p.bstages, p.aslots, p.epi_bufs);
         dev_prof_print(head, p.prof, st, pair);
     }
 #endif
