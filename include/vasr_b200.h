@@ -9,7 +9,11 @@
  * caller owns and keeps alive; work is enqueued on the cudaStream_t passed as
  * `stream` (a void*, 0 = legacy default stream) and no entry point
  * synchronises the device except vasr_model_finalize and the *_host calls.
- * A handle is not internally locked: one handle per module instance per device.
+ * Handles (vasr_frontend, vasr_model, vasr_lm, vasr_resampler) are NOT thread-safe and are single-stream: a handle
+ * owns scratch buffers, helper streams and cached descriptors, so concurrent calls on one handle from two host
+ * threads, or interleaved calls on two streams without the caller ordering them, are undefined.  Use one handle
+ * per module instance per host thread per device (the reference shares one instance across requests without a
+ * lock, app.py:22-28; a server doing that must serialise its calls).
  *
  * Activations inside the library are channels-last fp32:
  *     features [B, T_f, F]   activations [B, T, C]   log-probs [B, T_e, V+1]
@@ -49,14 +53,15 @@
 extern "C" {
 #endif
 
-#define VASR_ABI_VERSION 1
+#define VASR_ABI_VERSION 2
 
 typedef enum vasr_status {
     VASR_OK = 0,
     VASR_EINVAL = -1,     /* bad argument / unsupported configuration  (ValueError)   */
     VASR_ECUDA = -2,      /* CUDA runtime / driver error               (RuntimeError) */
     VASR_ESTATE = -3,     /* call order (e.g. forward before finalize) (RuntimeError) */
-    VASR_ENOMEM = -4      /* workspace too small / allocation failed   (RuntimeError) */
+    VASR_ENOMEM = -4,     /* workspace too small / allocation failed   (RuntimeError) */
+    VASR_ERANGE = -5      /* an activation left the range of the f16x3 / f16x1 operand format (RuntimeError) */
 } vasr_status;
 
 /* precision of the 1x1 (pointwise / residual / final) GEMMs of the encoder */
@@ -135,6 +140,12 @@ size_t vasr_encoder_workspace_bytes(const vasr_model* m, int B, int T_f);
 int  vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
                           float* enc, float* enc_len, void* workspace, size_t workspace_bytes,
                           void* stream);
+/* Range guard of the tensor-core modes.  f16x3 / f16x1 feed the 1x1 convolutions with fp16 operands; a depthwise
+ * output beyond +-65504 cannot be represented and would silently turn into inf/NaN and then - through ReLU - into
+ * zeros.  Every encoder kernel records that event in a status word inside `workspace`.  vasr_encoder_check
+ * synchronises `stream`, reads the word of the last vasr_encoder_forward that used `workspace` and returns
+ * VASR_ERANGE if it is set (VASR_OK otherwise; always VASR_OK in fp32 mode).  vasr_transcribe_host checks it itself. */
+int  vasr_encoder_check(vasr_model* m, void* workspace, size_t workspace_bytes, int B, void* stream);
 /* enc [B, T_e, C_out] -> log_probs [B, T_e, V+1] f32 (may be NULL), ids [B, T_e] i64 greedy argmax */
 int  vasr_decoder_forward(vasr_model* m, const float* enc, int B, int T_e,
                           float* log_probs, int64_t* ids, void* stream);
@@ -143,18 +154,23 @@ int  vasr_decoder_forward(vasr_model* m, const float* enc, int B, int T_e,
 int  vasr_greedy_argmax(const float* log_probs, int N, int V, int64_t* ids, void* stream);
 
 /* ---- greedy CTC collapse ---------------------------------------------- */
-/* ids [B, T] i64 -> out_ids [B, T] i32 (collapsed, -1 padded), out_len [B] i32; all T frames are used */
-int  vasr_ctc_collapse(const int64_t* ids, int B, int T, int blank,
+/* ids [B, T] i64 -> out_ids [B, T] i32 (collapsed, -1 padded), out_len [B] i32.
+ * frames [B] i32 (device) or NULL: utterance b is collapsed over its first min(frames[b], T) frames.  NULL = all T
+ * frames, which is what the reference does with the single utterance it is given (helpers.py:26-30); in a
+ * zero-padded batch pass vasr_model_out_frames(frontend frames of utterance b) so that every utterance is decoded
+ * over exactly the frames it would have had alone. */
+int  vasr_ctc_collapse(const int64_t* ids, const int32_t* frames, int B, int T, int blank,
                        int32_t* out_ids, int32_t* out_len, void* stream);
 
 /* ---- CTC prefix beam search, no language model ------------------------- */
 /* BeamSearchDecoderWithLM.forward with lm_path=None (beam_search_decoder.py:95-102 -> pyctcdecode decode()).
- * log_probs [B, T, V] f32 (all T frames are used, like the reference), blank = V-1 for NeMo vocabularies,
+ * log_probs [B, T, V] f32, frames [B] i32 or NULL as in vasr_ctc_collapse (NULL: all T frames are used, like the
+ * reference with its batch of one, beam_search_decoder.py:96-101), blank = V-1 for NeMo vocabularies,
  * space_id = index of ' ' in the vocabulary or -1.  out_ids [B, T] i32 (best text as symbol ids, -1 padded,
  * single spaces, no leading space), out_len [B] i32, out_score [B] f32 (log score, may be NULL).
  * beam_width <= 128; pyctcdecode defaults: token_min_logp = -5, beam_prune_logp = -10. */
 size_t vasr_ctc_beam_workspace_bytes(int B, int T);
-int  vasr_ctc_beam_search(const float* log_probs, int B, int T, int V, int blank, int space_id,
+int  vasr_ctc_beam_search(const float* log_probs, const int32_t* frames, int B, int T, int V, int blank, int space_id,
                           int beam_width, float token_min_logp, float beam_prune_logp,
                           void* workspace, size_t workspace_bytes,
                           int32_t* out_ids, int32_t* out_len, float* out_score, void* stream);
@@ -193,7 +209,7 @@ int  vasr_lm_score_batch(const vasr_lm* lm, const int32_t* ctx, const int32_t* n
  * before alpha; a text first completed at the end of the utterance also gets P(</s>).  pyctcdecode default
  * unk_score_offset = -10.  Labels must be single characters.  out_score = acoustic + LM score of the best text. */
 size_t vasr_ctc_beam_lm_workspace_bytes(int B, int T, int beam_width);
-int  vasr_ctc_beam_search_lm(const float* log_probs, int B, int T, int V, int blank, int space_id,
+int  vasr_ctc_beam_search_lm(const float* log_probs, const int32_t* frames, int B, int T, int V, int blank, int space_id,
                              int beam_width, float token_min_logp, float beam_prune_logp,
                              const vasr_lm* lm, double alpha, double beta, double unk_score_offset,
                              void* workspace, size_t workspace_bytes,

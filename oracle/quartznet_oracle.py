@@ -291,10 +291,30 @@ def greedy_argmax(log_probs: torch.Tensor) -> torch.Tensor:
     return log_probs.argmax(dim=-1, keepdim=False)
 
 
-def ctc_collapse(ids: np.ndarray, blank: int) -> List[List[int]]:
-    """helpers.py:20-32: iterate ALL frames (no length truncation)."""
+def utterance_frames(jasper_cfg: Sequence[dict], length, hop: int = 160) -> List[int]:
+    """Encoder frames each utterance has when the reference runs it ALONE (infer.py:167-171: one utterance per call):
+    T_f = 1 + L // hop (features.py:245-301, center=True, pad_to=0), then `(T + 2p - d(k-1) - 1) // s + 1` per
+    sub-block (parts/jasper.py:108-111).  A zero-padded batch is decoded utterance by utterance over these frames."""
     out = []
-    for row in np.asarray(ids):
+    for L in np.asarray(length).reshape(-1).tolist():
+        t = int(L) // hop + 1
+        for c in jasper_cfg:
+            k = c["kernel"][0] if isinstance(c["kernel"], (list, tuple)) else c["kernel"]
+            st = c["stride"][0] if isinstance(c.get("stride", 1), (list, tuple)) else c.get("stride", 1)
+            d = c["dilation"][0] if isinstance(c.get("dilation", 1), (list, tuple)) else c.get("dilation", 1)
+            for _ in range(int(c["repeat"])):
+                t = (t + 2 * get_same_padding(k, st, d) - d * (k - 1) - 1) // st + 1
+        out.append(max(t, 0))
+    return out
+
+
+def ctc_collapse(ids: np.ndarray, blank: int, frames: Optional[Sequence[int]] = None) -> List[List[int]]:
+    """helpers.py:20-32: iterate ALL frames of the utterance (no truncation at the encoded length).  `frames`: rows of a
+    zero-padded batch are cut to the frames the utterance has on its own (`utterance_frames`) first."""
+    out = []
+    for i, row in enumerate(np.asarray(ids)):
+        if frames is not None:
+            row = row[: int(frames[i])]
         dec = []
         prev = blank
         for p in row:

@@ -572,3 +572,101 @@ def test_engine_with_language_model():
     assert eng.transcribe(wave[2, : length[2]].numpy()) == BO.beam_search_lm(
         eng.forward_device(wave[2:3, : length[2]].cuda(), length[2:3].cuda(), want_log_probs=True)["log_probs"][0].cpu().numpy(),
         md["labels"], 100, ora)[0]
+
+
+# ----------------------------------------------------------------------------- round-2 regressions
+@pytest.mark.parametrize("B", [2, 80])
+def test_segment_descriptor_cache_keyed_on_strides(B):
+    """T_f = 2k and T_f = 2k - 1 give the same segment T = k but different batch strides and buffer offsets inside the
+    same workspace: a descriptor table cached for the first call must not be reused by the second (B = 2: 32-row
+    latency tiles, B = 80: the CTA-pair kernel).  Longest first, like `plan_batches` orders its batches."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("en15x5", "rand")
+    tc = _engine(V, md, enc_sd, dec_sd, "f16x3")
+    ref = _engine(V, md, enc_sd, dec_sd, "fp32")
+    g = torch.Generator().manual_seed(17)
+    for L in (199 * 160, 198 * 160, 199 * 160):                 # T_f = 200, 199, 200 -> T = 100 every time
+        wave = (0.1 * torch.randn(B, L, generator=g)).clamp_(-1, 1)
+        length = torch.full((B,), L, dtype=torch.int64)
+        length[-1] = L - 4000; wave[-1, L - 4000:] = 0
+        a = tc.forward_device(wave.cuda(), length.cuda(), want_log_probs=True)
+        b = ref.forward_device(wave.cuda(), length.cuda(), want_log_probs=True)
+        assert a["enc"].shape[1] == 100
+        rel = ((a["log_probs"] - b["log_probs"]).norm() / b["log_probs"].norm()).item()
+        assert rel < LOGIT_REL, (L, rel)
+        for u in range(B):                                        # every utterance, not just the first
+            r_u = ((a["enc"][u] - b["enc"][u]).norm() / b["enc"][u].norm()).item()
+            assert r_u < LOGIT_REL, (L, u, r_u)
+
+
+def test_ctc_collapse_with_utterance_frames():
+    V = _cuda()
+    g = np.random.default_rng(3)
+    B, T, blank = 5, 300, 28
+    ids = torch.from_numpy(g.integers(0, blank + 1, size=(B, T)))
+    frames = [300, 1, 0, 257, 123]
+    out, n = V.ctc_collapse(ids.cuda(), blank, frames=torch.tensor(frames))
+    want = O.ctc_collapse(ids.numpy(), blank, frames=frames)
+    got = [row[:k].tolist() for row, k in zip(out.cpu().numpy(), n.cpu().numpy())]
+    assert got == want
+    assert (out.cpu().numpy()[2] == -1).all()
+
+
+def test_batch_of_n_equals_n_single_utterance_calls():
+    """A transcript must not depend on what else is in the batch (the reference transcribes one utterance per call,
+    infer.py:167-171, beam_search_decoder.py:96): greedy ids, collapsed ids and beam-search output of a ragged
+    zero-padded batch equal those of every utterance run alone.  Lengths are multiples of the hop: otherwise the last
+    feature frame of a shorter utterance sees zero padding in the batch and reflect padding when alone
+    (torch.stft on the padded row, features.py:181-188) - the reference's own batched semantics."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "rand")
+    eng = _engine(V, md, enc_sd, dec_sd, "f16x3")
+    lens = [48000, 32000, 160 * 111, 160 * 250, 160 * 37]
+    g = torch.Generator().manual_seed(23)
+    L = max(lens)
+    wave = torch.zeros((len(lens), L))
+    for i, n in enumerate(lens):
+        wave[i, :n] = (0.1 * torch.randn(n, generator=g)).clamp_(-1, 1)
+    length = torch.tensor(lens, dtype=torch.int64)
+    r = eng.forward_device(wave.cuda(), length.cuda(), want_log_probs=True)
+    frames = r["frames"].cpu().tolist()
+    assert frames == O.utterance_frames(md["JasperEncoder"]["jasper"], lens)
+    beam_batch = eng.beam.decode_batch(r["log_probs"], frames=r["frames"])
+    out, n = r["out_ids"].cpu().numpy(), r["out_len"].cpu().numpy()
+    for i, nl in enumerate(lens):
+        one = eng.forward_device(wave[i:i + 1, :nl].cuda(), length[i:i + 1].cuda(), want_log_probs=True)
+        f = frames[i]
+        assert one["ids"].shape[1] == f
+        assert torch.equal(one["ids"][0], r["ids"][i, :f]), i
+        assert torch.equal(one["log_probs"][0], r["log_probs"][i, :f]), i
+        assert out[i, : n[i]].tolist() == one["out_ids"][0, : int(one["out_len"][0])].cpu().tolist(), i
+        assert eng.beam.decode_batch(one["log_probs"]) == [beam_batch[i]], i
+    # host route: same collapsed ids
+    ids_h, len_h = eng.transcribe_host_ids(wave.pin_memory(), length.pin_memory())
+    assert [row[:k].tolist() for row, k in zip(ids_h.numpy(), len_h.numpy())] == [out[i, : n[i]].tolist() for i in range(len(lens))]
+
+
+def test_range_guard_reports_fp16_overflow():
+    """f16x3 / f16x1 feed the tensor cores fp16 operands: a depthwise output beyond 65504 must surface as an error, not
+    as silently wrong (NaN -> ReLU -> 0) activations.  fp32 mode has no such limit."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "rand")
+    big = dict(enc_sd)
+    big["encoder.3.mconv.0.conv.weight"] = enc_sd["encoder.3.mconv.0.conv.weight"] * 3e6      # depthwise taps of block 3
+    g = torch.Generator().manual_seed(29)
+    wave = (0.1 * torch.randn(3, 32000, generator=g)).clamp_(-1, 1)
+    length = torch.tensor([32000, 30000, 16000]); wave[1, 30000:] = 0; wave[2, 16000:] = 0
+    ok = _engine(V, md, enc_sd, dec_sd, "f16x3")
+    ok.transcribe_batch_device(wave.cuda(), length.cuda())                                     # in range: no error
+    ok.transcribe_host_ids(wave.pin_memory(), length.pin_memory())
+    bad = _engine(V, md, big, dec_sd, "f16x3")
+    with pytest.raises(RuntimeError, match="fp16 range"):
+        bad.transcribe_batch_device(wave.cuda(), length.cuda())
+    with pytest.raises(RuntimeError, match="fp16 range"):
+        bad.transcribe_host_ids(wave.pin_memory(), length.pin_memory())
+    for B in (80,):                                                                            # CTA-pair kernel too
+        w80 = wave[:1].repeat(B, 1)
+        with pytest.raises(RuntimeError, match="fp16 range"):
+            bad.transcribe_batch_device(w80.cuda(), torch.full((B,), 32000))
+    fp = _engine(V, md, big, dec_sd, "fp32")
+    fp.transcribe_batch_device(wave.cuda(), length.cuda())

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libvasr_b200.so does not export {s}"
     assert sorted(_lib.PROTOTYPES) == syms, "python prototypes out of sync with include/vasr_b200.h"
-    assert _lib.load().vasr_abi_version() == 1
+    assert _lib.load().vasr_abi_version() == 2
 
 
 def test_model_create_validation_no_gpu_needed():

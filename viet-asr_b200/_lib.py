@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # VASR_B200_LIB: developer override to time an experimental build of the same library (tools/); never a fallback
 LIB_PATH = os.environ.get("VASR_B200_LIB") or os.path.join(_HERE, "libvasr_b200.so")
 
-VASR_OK, VASR_EINVAL, VASR_ECUDA, VASR_ESTATE, VASR_ENOMEM = 0, -1, -2, -3, -4
+VASR_OK, VASR_EINVAL, VASR_ECUDA, VASR_ESTATE, VASR_ENOMEM, VASR_ERANGE = 0, -1, -2, -3, -4, -5
 GEMM_FP32_SIMT, GEMM_F16X3, GEMM_F16X1 = 0, 1, 2
 GEMM_MODES = {"fp32": GEMM_FP32_SIMT, "f16x3": GEMM_F16X3, "f16x1": GEMM_F16X1}
 
@@ -61,18 +61,19 @@ PROTOTYPES = {
     "vasr_model_num_classes": (_i, [_vp]),
     "vasr_encoder_workspace_bytes": (_sz, [_vp, _i, _i]),
     "vasr_encoder_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "vasr_encoder_check": (_i, [_vp, _vp, _sz, _i, _vp]),
     "vasr_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "vasr_greedy_argmax": (_i, [_vp, _i, _i, _vp, _vp]),
-    "vasr_ctc_collapse": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "vasr_ctc_collapse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "vasr_ctc_beam_workspace_bytes": (_sz, [_i, _i]),
-    "vasr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "vasr_ctc_beam_search": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vasr_lm_create": (_i, [C.POINTER(LmArrays), C.POINTER(_vp)]),
     "vasr_lm_destroy": (None, [_vp]),
     "vasr_lm_order": (_i, [_vp]),
     "vasr_lm_hash_labels": (C.c_uint64, [_vp, _i]),
     "vasr_lm_score_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vasr_ctc_beam_lm_workspace_bytes": (_sz, [_i, _i, _i]),
-    "vasr_ctc_beam_search_lm": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, C.c_double, C.c_double,
+    "vasr_ctc_beam_search_lm": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, C.c_double, C.c_double,
                                      C.c_double, _vp, _sz, _vp, _vp, _vp, _vp]),
     "vasr_resampler_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "vasr_resampler_destroy": (None, [_vp]),
@@ -99,7 +100,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.vasr_abi_version() != 1:
+    if lib.vasr_abi_version() != 2:
         raise RuntimeError("libvasr_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -370,6 +370,26 @@ class JasperEncoder(TrainableNM):
     def out_frames(self, T_f: int) -> int:
         return int(self._handle().lib.vasr_model_out_frames(self._handle().h, int(T_f)))
 
+    def out_frames_of(self, feat_frames: torch.Tensor) -> torch.Tensor:
+        """Per-utterance T_e for per-utterance feature-frame counts [B] (int tensor, any device): the conv arithmetic
+        of `MaskedConv1d.get_seq_len` (parts/jasper.py:108-111) on integers, block by block."""
+        t = feat_frames.to(torch.int64)
+        for c in self._jasper:
+            first = lambda v: int(v[0] if isinstance(v, (list, tuple)) else v)
+            k, s_, d = first(c["kernel"]), first(c.get("stride", 1)), first(c.get("dilation", 1))
+            pad = (d * k) // 2 - 1 if d > 1 else k // 2
+            for _ in range(int(c["repeat"])):
+                t = torch.div(t + 2 * pad - d * (k - 1) - 1, s_, rounding_mode="floor") + 1
+        return t.clamp_(min=0).to(torch.int32)
+
+    def check_range(self, B: int):
+        """Raise RuntimeError if the last forward on this module overflowed the fp16 operand range of the tensor-core
+        modes (synchronises the current stream; see vasr_encoder_check in include/vasr_b200.h)."""
+        if self._ws is None or self._model is None:
+            return
+        h = self._model
+        _lib.check(h.lib.vasr_encoder_check(h.h, self._ws.data_ptr(), self._ws.numel(), int(B), _stream_ptr()))
+
     def forward_channels_last(self, feat: torch.Tensor, length: torch.Tensor):
         """feat [B, T_f, feat_in] contiguous fp32, length [B] -> enc [B, T_e, C], enc_len [B] f32."""
         _require_cuda(feat, "JasperEncoder")
@@ -546,14 +566,26 @@ class NGramLM:
         return out
 
 
+def _frames_arg(frames, B: int, device):
+    """Optional per-utterance frame counts -> (tensor kept alive, device pointer or None)."""
+    if frames is None:
+        return None, None
+    f = torch.as_tensor(frames).to(device=device, dtype=torch.int32).contiguous()
+    if f.shape != (B,):
+        raise ValueError(f"frames must have shape [{B}], got {tuple(f.shape)}")
+    return f, f.data_ptr()
+
+
 def ctc_beam_search(log_probs: torch.Tensor, vocab: Sequence[str], beam_width: int,
                     token_min_logp: float = -5.0, beam_prune_logp: float = -10.0, lm: Optional[NGramLM] = None,
-                    alpha: float = 0.5, beta: float = 1.5, unk_score_offset: float = -10.0):
+                    alpha: float = 0.5, beta: float = 1.5, unk_score_offset: float = -10.0, frames=None):
     """Device prefix beam search, optionally with n-gram LM fusion: log_probs [B, T, V+1] ->
-    (ids [B, T] i32, len [B] i32, score [B] f32)."""
+    (ids [B, T] i32, len [B] i32, score [B] f32).  `frames` [B]: utterance b is searched over its first frames[b]
+    frames only (a zero-padded batch; None = all T frames, the reference's single-utterance behaviour)."""
     _require_cuda(log_probs, "ctc_beam_search")
     lp = log_probs.to(torch.float32).contiguous()
     B, T, V1 = lp.shape
+    fr, fr_ptr = _frames_arg(frames, B, lp.device)
     if V1 != len(vocab) + 1:
         raise ValueError(f"log_probs has {V1} classes but the vocabulary has {len(vocab)} labels (+1 blank)")
     lib = _lib.load()
@@ -563,13 +595,13 @@ def ctc_beam_search(log_probs: torch.Tensor, vocab: Sequence[str], beam_width: i
     space_id = list(vocab).index(" ") if " " in vocab else -1
     if lm is None:
         ws = torch.empty((int(lib.vasr_ctc_beam_workspace_bytes(B, T)),), dtype=torch.uint8, device=lp.device)
-        _lib.check(lib.vasr_ctc_beam_search(lp.data_ptr(), B, T, V1, len(vocab), space_id, int(beam_width),
+        _lib.check(lib.vasr_ctc_beam_search(lp.data_ptr(), fr_ptr, B, T, V1, len(vocab), space_id, int(beam_width),
                                             float(token_min_logp), float(beam_prune_logp), ws.data_ptr(), ws.numel(),
                                             ids.data_ptr(), n.data_ptr(), sc.data_ptr(), _stream_ptr()))
     else:
         nbytes = int(lib.vasr_ctc_beam_lm_workspace_bytes(B, T, int(beam_width)))
         ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=lp.device)
-        _lib.check(lib.vasr_ctc_beam_search_lm(lp.data_ptr(), B, T, V1, len(vocab), space_id, int(beam_width),
+        _lib.check(lib.vasr_ctc_beam_search_lm(lp.data_ptr(), fr_ptr, B, T, V1, len(vocab), space_id, int(beam_width),
                                                float(token_min_logp), float(beam_prune_logp), lm._h, float(alpha),
                                                float(beta), float(unk_score_offset), ws.data_ptr(), ws.numel(),
                                                ids.data_ptr(), n.data_ptr(), sc.data_ptr(), _stream_ptr()))
@@ -608,8 +640,11 @@ class BeamSearchDecoderWithLM(NonTrainableNM):
         self.lm_path = lm_path
         self.lm = NGramLM(lm_path, self.vocab) if lm_path is not None else None
 
-    def decode_batch(self, log_probs) -> List[str]:
-        ids, n, _ = ctc_beam_search(log_probs, self.vocab, self.beam_width, lm=self.lm, alpha=self.alpha, beta=self.beta)
+    def decode_batch(self, log_probs, frames=None) -> List[str]:
+        """`frames` [B]: frames of every utterance in a zero-padded batch (each is decoded as if it were alone, which
+        is the only way the reference ever runs this decoder, :96); None = all frames of the tensor."""
+        ids, n, _ = ctc_beam_search(log_probs, self.vocab, self.beam_width, lm=self.lm, alpha=self.alpha, beta=self.beta,
+                                    frames=frames)
         return [" ".join(t.split()) for t in ids_to_text(ids, n, self.vocab)]
 
     def forward(self, log_probs, log_probs_length=None):
@@ -618,15 +653,17 @@ class BeamSearchDecoderWithLM(NonTrainableNM):
 
 
 # --------------------------------------------------------------------------- helpers.py
-def ctc_collapse(predictions: torch.Tensor, blank: int):
-    """Device CTC collapse -> (ids [B, T] int32 padded with -1, lengths [B] int32)."""
+def ctc_collapse(predictions: torch.Tensor, blank: int, frames=None):
+    """Device CTC collapse -> (ids [B, T] int32 padded with -1, lengths [B] int32).  `frames` [B]: see
+    `ctc_beam_search` (None = all T frames, helpers.py:26-30)."""
     _require_cuda(predictions, "ctc_collapse")
     p = predictions.to(torch.int64).contiguous()
     B, T = p.shape
+    fr, fr_ptr = _frames_arg(frames, B, p.device)
     out = torch.empty((B, T), dtype=torch.int32, device=p.device)
     n = torch.empty((B,), dtype=torch.int32, device=p.device)
     lib = _lib.load()
-    _lib.check(lib.vasr_ctc_collapse(p.data_ptr(), B, T, int(blank), out.data_ptr(), n.data_ptr(), _stream_ptr()))
+    _lib.check(lib.vasr_ctc_collapse(p.data_ptr(), fr_ptr, B, T, int(blank), out.data_ptr(), n.data_ptr(), _stream_ptr()))
     return out, n
 
 

@@ -25,6 +25,7 @@ struct vasr_resampler {
     double* d_time = nullptr;   // [time_cap] resampy's running sum time_register[t] for time_inc
     long long time_cap = 0;
     double time_inc = 0.0;
+    cudaEvent_t time_ready = nullptr;   // recorded after the table was (re)built; later calls on any stream wait for it
 };
 
 namespace vasr {
@@ -140,6 +141,7 @@ extern "C" void vasr_resampler_destroy(vasr_resampler* rs)
 {
     if (!rs) return;
     cudaFree(rs->d_win); cudaFree(rs->d_delta); cudaFree(rs->d_time);
+    if (rs->time_ready) cudaEventDestroy(rs->time_ready);
     delete rs;
 }
 
@@ -189,6 +191,11 @@ extern "C" int vasr_resample(vasr_resampler* rs, const void* x, int pcm16, const
         rs->d_time = t; rs->time_cap = cap; rs->time_inc = inc;
         time_table_kernel<<<1, 32, 0, st>>>(rs->d_time, cap, inc);
         VASR_LAUNCH_OK("time_table_kernel");
+        if (!rs->time_ready) VASR_CUDA_OK(cudaEventCreateWithFlags(&rs->time_ready, cudaEventDisableTiming));
+        VASR_CUDA_OK(cudaEventRecord(rs->time_ready, st));
+    } else if (rs->time_ready) {
+        // the table may have been built on another stream: order this stream's reads after it
+        VASR_CUDA_OK(cudaStreamWaitEvent(st, rs->time_ready, 0));
     }
     if (pcm16)
         resample_kernel<int16_t><<<grid, 128, 0, st>>>((const int16_t*)x, (const long long*)len_in, (long long)L_in, y,

@@ -194,7 +194,7 @@ struct Smem {
 
 template <bool LM>
 __global__ void __launch_bounds__(THREADS)
-beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_id, int beam_width,
+beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int T, int V1, int blank, int space_id, int beam_width,
             float tok_min, float prune, unsigned char* __restrict__ bp_parent, unsigned char* __restrict__ bp_sym,
             int* __restrict__ out_ids, int* __restrict__ out_len, float* __restrict__ out_score,
             const DeviceLM lm, const LmParams q)
@@ -208,6 +208,9 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
     unsigned long long* seen = LM ? q.seen + (size_t)b * q.seen_cap : nullptr;
     const float clip_lo = logf(1e-15f);
     const int nkeep = LM ? lm.order - 1 : 0;               // KenLM context length
+    // frames of THIS utterance: a zero-padded batch must decode every utterance over the frames the reference sees
+    // when it runs that utterance alone (beam_search_decoder.py:96 asserts batch size 1), not over the padding
+    const int Tb = frames ? min(max(frames[b], 0), T) : T;
 
     if (tid == 0) {
         s.hash[0] = H0; s.fhash[0] = H0; s.score[0] = 0.0; s.lastsym[0] = SYM_NONE; s.lastkey[0] = KEY_NONE; s.nbeam = 1;
@@ -236,7 +239,7 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
         s.commit_lm[i] = lm_accumulate(q, s.lmscore[i], r);
     };
 
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < Tb; ++t) {
         // ---- 1. frame log-probs (clipped like log(clip(p, 1e-15, 1))) and candidate symbols -------------------
         if (tid < V1) s.lp[tid] = fminf(fmaxf(lpb[(size_t)t * V1 + tid], clip_lo), 0.f);
         __syncthreads();
@@ -463,7 +466,7 @@ beam_kernel(const float* __restrict__ logp, int T, int V1, int blank, int space_
         }
         int* oid = out_ids + (size_t)b * T;
         int len = 0, k = bi;
-        for (int t = T - 1; t >= 0; --t) {
+        for (int t = Tb - 1; t >= 0; --t) {
             const int app = bps[(size_t)t * BW_MAX + k];
             if (app != SYM_NONE) oid[len++] = app;         // reversed
             k = bpp[(size_t)t * BW_MAX + k];
@@ -602,7 +605,7 @@ extern "C" size_t vasr_ctc_beam_lm_workspace_bytes(int B, int T, int beam_width)
     return bp + (size_t)B * seen_capacity(T, beam_width) * sizeof(unsigned long long);
 }
 
-static int beam_launch(const float* log_probs, int B, int T, int V1, int blank, int space_id, int beam_width,
+static int beam_launch(const float* log_probs, const int32_t* frames, int B, int T, int V1, int blank, int space_id, int beam_width,
                        float token_min_logp, float beam_prune_logp, const vasr_lm* lm, double alpha, double beta,
                        double unk_score_offset, void* workspace, size_t workspace_bytes,
                        int32_t* out_ids, int32_t* out_len, float* out_score, void* stream, const char* who)
@@ -635,33 +638,33 @@ static int beam_launch(const float* log_probs, int B, int T, int V1, int blank, 
         q.seen = (unsigned long long*)((unsigned char*)workspace + bp);
         q.seen_cap = (int)seen_capacity(T, beam_width);
         VASR_CUDA_OK(cudaMemsetAsync(q.seen, 0, (size_t)B * q.seen_cap * sizeof(unsigned long long), st));
-        beam_kernel<true><<<B, THREADS, smem, st>>>(log_probs, T, V1, blank, space_id, beam_width, token_min_logp,
+        beam_kernel<true><<<B, THREADS, smem, st>>>(log_probs, frames, T, V1, blank, space_id, beam_width, token_min_logp,
                                                     beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score, lm->dev, q);
     } else {
-        beam_kernel<false><<<B, THREADS, smem, st>>>(log_probs, T, V1, blank, space_id, beam_width, token_min_logp,
+        beam_kernel<false><<<B, THREADS, smem, st>>>(log_probs, frames, T, V1, blank, space_id, beam_width, token_min_logp,
                                                      beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score, DeviceLM{}, q);
     }
     VASR_LAUNCH_OK("beam_kernel");
     return VASR_OK;
 }
 
-extern "C" int vasr_ctc_beam_search(const float* log_probs, int B, int T, int V1, int blank, int space_id,
+extern "C" int vasr_ctc_beam_search(const float* log_probs, const int32_t* frames, int B, int T, int V1, int blank, int space_id,
                                     int beam_width, float token_min_logp, float beam_prune_logp,
                                     void* workspace, size_t workspace_bytes,
                                     int32_t* out_ids, int32_t* out_len, float* out_score, void* stream)
 {
-    return beam_launch(log_probs, B, T, V1, blank, space_id, beam_width, token_min_logp, beam_prune_logp, nullptr, 0.0, 0.0,
+    return beam_launch(log_probs, frames, B, T, V1, blank, space_id, beam_width, token_min_logp, beam_prune_logp, nullptr, 0.0, 0.0,
                        0.0, workspace, workspace_bytes, out_ids, out_len, out_score, stream, "vasr_ctc_beam_search");
 }
 
-extern "C" int vasr_ctc_beam_search_lm(const float* log_probs, int B, int T, int V1, int blank, int space_id,
+extern "C" int vasr_ctc_beam_search_lm(const float* log_probs, const int32_t* frames, int B, int T, int V1, int blank, int space_id,
                                        int beam_width, float token_min_logp, float beam_prune_logp,
                                        const vasr_lm* lm, double alpha, double beta, double unk_score_offset,
                                        void* workspace, size_t workspace_bytes,
                                        int32_t* out_ids, int32_t* out_len, float* out_score, void* stream)
 {
     VASR_REQUIRE(lm, "vasr_ctc_beam_search_lm: null language model");
-    return beam_launch(log_probs, B, T, V1, blank, space_id, beam_width, token_min_logp, beam_prune_logp, lm, alpha, beta,
+    return beam_launch(log_probs, frames, B, T, V1, blank, space_id, beam_width, token_min_logp, beam_prune_logp, lm, alpha, beta,
                        unk_score_offset, workspace, workspace_bytes, out_ids, out_len, out_score, stream,
                        "vasr_ctc_beam_search_lm");
 }

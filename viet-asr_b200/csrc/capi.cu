@@ -28,7 +28,8 @@ int set_error(int code, const char* fmt, ...)
 struct HostTensor { std::vector<int64_t> dims; std::vector<float> data; };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr size_t TILE_COUNTER_BYTES = 8192;   // one int per (layer, sub-batch) launch of the persistent kernels
+constexpr size_t TILE_COUNTER_BYTES = 8192;   // one int per (layer, sub-batch) launch of the persistent kernels; the last int is the range-guard status word
+constexpr size_t STATUS_WORD = TILE_COUNTER_BYTES / sizeof(int) - 1;
 // tile counters + the (layer, utterance) completion counters of the multi-layer segment kernels; zeroed per forward
 static inline size_t sync_region_bytes(size_t n_layers, int B) { return TILE_COUNTER_BYTES + align_up(n_layers * (size_t)B * sizeof(int), 256); }
 
@@ -336,8 +337,7 @@ namespace vasr {
 static int pick_nsub(const vasr_model* m, int B, int T_f)
 {
     if (m->gemm_mode == VASR_GEMM_FP32_SIMT) return 1;
-    const char* env = getenv("VASR_SUBSTREAMS");
-    int want = env ? atoi(env) : m->max_sub;
+    int want = dev_env_int("VASR_SUBSTREAMS", m->max_sub);
     if (want < 1) want = 1;
     if (want > 8) want = 8;
     const int tiles_per_utt = ceil_div(vasr_model_out_frames(m, T_f), 128);
@@ -372,7 +372,8 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
     float* P[3] = {(float*)(ws + lens_b), (float*)(ws + lens_b + act), (float*)(ws + lens_b + 2 * act)};
     float* DW = (float*)(ws + lens_b + 3 * act);
     int rc;
-    VASR_REQUIRE(m->layers.size() * 8 * sizeof(int) <= TILE_COUNTER_BYTES, "too many layers for the tile-counter table");
+    VASR_REQUIRE(m->layers.size() * 8 < STATUS_WORD, "too many layers for the tile-counter table");
+    int* status = counters + STATUS_WORD;
     if (!sub_ready) {
         if (m->gemm_mode != VASR_GEMM_FP32_SIMT) VASR_CUDA_OK(cudaMemsetAsync(counters, 0, sync_b, st));
         if ((rc = launch_lens((const long long*)seq_len, B, 0, B, m->n_stage, m->d_st_k, m->d_st_s, m->d_st_d, m->d_st_p,
@@ -404,10 +405,7 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
         }
     }
 
-    // VASR_GRID_SPLIT=1: each of the nsub concurrent kernels gets 1/nsub of the SMs (kernels of different sub-batches
-    // then run side by side, out of phase, instead of back to back)
-    int grid_limit = 0;
-    if (nsub > 1) { const char* e = getenv("VASR_GRID_SPLIT"); if (e && atoi(e) > 0) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); grid_limit = sms / nsub; } }
+    const int grid_limit = 0;       // every launch may use all SMs (persistent kernels of the sub-batches take turns)
     // ---- plan: buffers and shapes of every layer (3 rotating buffers; the output never aliases the layer's input
     // or the block input).  Tensor path: every utterance owns a FIXED region of each rotating buffer (batch stride
     // T_f * cmax), whatever the layer's T and C.  Sub-batches run on their own streams and may be several layers
@@ -446,9 +444,9 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
             }
         }
     }
-    static int mega = -1;
-    if (mega < 0) { const char* e = getenv("VASR_TC_MEGA"); mega = (e && atoi(e) == 0) ? 0 : 1; }
+    const int mega = dev_env_int("VASR_TC_MEGA", 1);       // developer builds: 0 = one launch per sub-block
     const int split3 = m->gemm_mode == VASR_GEMM_F16X3;
+    auto run_layers = [&]() -> int {
     for (size_t i = 0; i < plan.size();) {
         // longest run of layers that one segment kernel can execute
         size_t j = i;
@@ -470,7 +468,7 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
                 const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
                 if (b1 == b0) continue;
                 if ((rc = launch_segment_tc(seg.data(), (int)seg.size(), B, plan[i].T, split3, b0, b1 - b0,
-                                            counters + plan[i].li * 8 + s2, done + plan[i].li * (size_t)B, B, grid_limit,
+                                            counters + plan[i].li * 8 + s2, status, done + plan[i].li * (size_t)B, B, grid_limit,
                                             nsub > 1 ? m->sub_streams[s2] : st))) return rc;
             }
             i = j;
@@ -483,7 +481,7 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
                 const int b0 = (int)((long long)B * s2 / nsub), b1 = (int)((long long)B * (s2 + 1) / nsub);
                 if (b1 == b0) continue;
                 if ((rc = launch_subblock_tc(sb, pl.cur, pl.xs, pl.res, pl.rs, pl.out, pl.ys, B, pl.T, pl.T_out, pl.len_in, pl.len_out,
-                                             split3, b0, b1 - b0, counters + pl.li * 8 + s2, grid_limit,
+                                             split3, b0, b1 - b0, counters + pl.li * 8 + s2, status, grid_limit,
                                              nsub > 1 ? m->sub_streams[s2] : st))) return rc;
             }
         } else {
@@ -498,12 +496,18 @@ static int encoder_forward_impl(vasr_model* m, const float* feat, const int64_t*
         }
         ++i;
     }
+    return VASR_OK;
+    };
+    rc = run_layers();
+    // join the sub-batch streams back into the caller's stream - also when a launch failed half-way, so that the
+    // caller's stream never runs ahead of work that was already enqueued on them
     if (nsub > 1)
         for (int s2 = 0; s2 < nsub; ++s2) {
-            VASR_CUDA_OK(cudaEventRecord(m->sub_events[s2], m->sub_streams[s2]));
-            VASR_CUDA_OK(cudaStreamWaitEvent(st, m->sub_events[s2], 0));
+            const cudaError_t e1 = cudaEventRecord(m->sub_events[s2], m->sub_streams[s2]);
+            const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(st, m->sub_events[s2], 0) : e1;
+            if (e2 != cudaSuccess && rc == VASR_OK) rc = set_error(VASR_ECUDA, "joining sub-batch stream %d failed: %s", s2, cudaGetErrorString(e2));
         }
-    return VASR_OK;
+    return rc;
 }
 
 extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int64_t* seq_len, int B, int T_f,
@@ -511,6 +515,24 @@ extern "C" int vasr_encoder_forward(vasr_model* m, const float* feat, const int6
                                     void* stream)
 {
     return encoder_forward_impl(m, feat, seq_len, B, T_f, enc, enc_len, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int vasr_encoder_check(vasr_model* m, void* workspace, size_t workspace_bytes, int B, void* stream)
+{
+    using namespace vasr;
+    VASR_REQUIRE(m && workspace && B > 0, "vasr_encoder_check: bad argument");
+    if (!m->finalized) return set_error(VASR_ESTATE, "vasr_encoder_check: weights not finalized");
+    if (m->gemm_mode == VASR_GEMM_FP32_SIMT) { VASR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream)); return VASR_OK; }
+    const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
+    VASR_REQUIRE(workspace_bytes >= lens_b + TILE_COUNTER_BYTES, "vasr_encoder_check: workspace too small");
+    int flag = 0;
+    VASR_CUDA_OK(cudaMemcpyAsync(&flag, (const char*)workspace + lens_b + STATUS_WORD * sizeof(int), sizeof(int),
+                                 cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VASR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag)
+        return set_error(VASR_ERANGE, "encoder: a depthwise-convolution output exceeded the fp16 range (|x| >= 65520) of the "
+                                      "f16x3/f16x1 operand format; results are invalid - use gemm_mode fp32 for this checkpoint");
+    return VASR_OK;
 }
 
 extern "C" int vasr_decoder_forward(vasr_model* m, const float* enc, int B, int T_e,
@@ -552,6 +574,7 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
     const size_t o_ids = take((size_t)B * T_e * sizeof(int64_t));
     const size_t o_oid = take((size_t)B * T_e * sizeof(int32_t));
     const size_t o_olen = take((size_t)B * sizeof(int32_t));
+    const size_t o_frames = take((size_t)B * sizeof(int32_t));
     const size_t o_ws = take(ws_b);
     if (off > m->scratch_bytes) {
         VASR_CUDA_OK(cudaStreamSynchronize(st));
@@ -563,17 +586,6 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
     char* s = (char*)m->scratch;
     int rc;
     const int nsub = pick_nsub(m, B, T_f);
-    cudaStream_t st_user = st;
-    {
-        const char* e8 = getenv("VASR_PIPE_DBG");
-        if (e8 && (atoi(e8) & 8) && nsub >= 2) {
-            static cudaStream_t ms = nullptr; static cudaEvent_t ev_in = nullptr;
-            if (!ms) { VASR_CUDA_OK(cudaStreamCreateWithFlags(&ms, cudaStreamNonBlocking)); VASR_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming)); }
-            VASR_CUDA_OK(cudaEventRecord(ev_in, st_user));
-            VASR_CUDA_OK(cudaStreamWaitEvent(ms, ev_in, 0));
-            st = ms;
-        }
-    }
     if (nsub < 2) {
         VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave, wave_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
         VASR_CUDA_OK(cudaMemcpyAsync(s + o_len, length_host, (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -605,9 +617,6 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
                                          (size_t)(b1 - b0) * sizeof(int64_t), cudaMemcpyHostToDevice, m->copy_stream));
             VASR_CUDA_OK(cudaEventRecord(m->copied[h], m->copy_stream));
         }
-        const char* pdbg_e = getenv("VASR_PIPE_DBG");
-        const int pdbg = pdbg_e ? atoi(pdbg_e) : 0;
-        if (pdbg & 1) VASR_CUDA_OK(cudaStreamSynchronize(m->copy_stream));
         for (int h = 0; h < nsub; ++h) {
             const int b0 = (int)((long long)B * h / nsub), b1 = (int)((long long)B * (h + 1) / nsub);
             VASR_CUDA_OK(cudaStreamWaitEvent(st, m->copied[h], 0));
@@ -615,19 +624,28 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
                                             b1 - b0, L, (float*)(s + o_feat) + (size_t)b0 * T_f * m->feat_in,
                                             (int64_t*)(s + o_seq) + b0, st))) return rc;
             VASR_CUDA_OK(cudaEventRecord(m->ready[h], st));
-            if (pdbg & 2) VASR_CUDA_OK(cudaStreamSynchronize(st));
         }
-        if (pdbg & 4) for (int h = 0; h < nsub; ++h) VASR_CUDA_OK(cudaEventRecord(m->ready[h], st));   // every sub-batch waits for all front ends
         if ((rc = encoder_forward_impl(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
                                        (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st, m->ready))) return rc;
     }
     if ((rc = vasr_decoder_forward(m, (const float*)(s + o_enc), B, T_e, nullptr, (int64_t*)(s + o_ids), st))) return rc;
-    if ((rc = vasr_ctc_collapse((const int64_t*)(s + o_ids), B, T_e, m->num_classes - 1, (int32_t*)(s + o_oid),
-                                (int32_t*)(s + o_olen), st))) return rc;
+    // every utterance is collapsed over the frames it would have had alone (the reference transcribes one utterance per
+    // call, infer.py:167-171): T_e of its own length, not of the batch's padded length
+    std::vector<int32_t> frames((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        int64_t lb = length_host[b];
+        if (lb > L) lb = L;
+        const int tf = lb > 0 ? vasr_frontend_num_frames(fe, lb) : 0;
+        frames[b] = tf > 0 ? vasr_model_out_frames(m, tf) : 0;
+    }
+    VASR_CUDA_OK(cudaMemcpyAsync(s + o_frames, frames.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if ((rc = vasr_ctc_collapse((const int64_t*)(s + o_ids), (const int32_t*)(s + o_frames), B, T_e, m->num_classes - 1,
+                                (int32_t*)(s + o_oid), (int32_t*)(s + o_olen), st))) return rc;
     VASR_CUDA_OK(cudaMemcpyAsync(out_ids_host, s + o_oid, (size_t)B * T_e * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VASR_CUDA_OK(cudaMemcpyAsync(out_len_host, s + o_olen, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VASR_CUDA_OK(cudaStreamSynchronize(st));
-    (void)st_user;
+    if ((rc = vasr_encoder_check(m, s + o_ws, ws_b, B, st))) return rc;      // VASR_ERANGE on fp16 overflow (tensor-core modes)
+#ifdef VASR_DEV
     if (const char* dump = getenv("VASR_HOST_DUMP")) {       // debugging aid: intermediate tensors of the host route
         auto dump_buf = [&](const char* name, size_t off_b, size_t bytes) {
             std::vector<char> h(bytes);
@@ -642,5 +660,6 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
         dump_buf("ids.bin", o_ids, (size_t)B * T_e * sizeof(int64_t));
         dump_buf("lens.bin", o_ws, (size_t)(m->n_stage + 1) * B * sizeof(int));
     }
+#endif
     return VASR_OK;
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string>
 #include <atomic>
 
@@ -39,6 +40,14 @@ extern std::atomic<long long> g_launch_count;
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Developer switches exist in libvasr_b200_dev.so only (-DVASR_DEV, `make dev`); the product library never reads the
+// environment on the compute path.
+#ifdef VASR_DEV
+static inline int dev_env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+static inline int dev_env_int(const char*, int dflt) { return dflt; }
+#endif
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------

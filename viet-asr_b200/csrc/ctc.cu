@@ -1,5 +1,6 @@
 // Greedy CTC collapse: drop repeats, then blanks (nemo/collections/asr/helpers.py:20-32).
-// All T frames are used - the reference does not truncate at the encoded length.
+// The reference uses every frame of the tensor it is given and only ever sees one utterance (infer.py:167-171); in a
+// zero-padded batch `frames[b]` restricts utterance b to the frames it would have had alone (null = all T frames).
 #include "common.cuh"
 #include "kernels.cuh"
 #include <math.h>
@@ -8,7 +9,7 @@ namespace vasr {
 
 // one CTA (256 threads) per utterance; ordered compaction via ballot + block prefix sum
 __global__ void __launch_bounds__(256)
-ctc_collapse_kernel(const long long* __restrict__ ids, int T, int blank,
+ctc_collapse_kernel(const long long* __restrict__ ids, const int* __restrict__ frames, int T, int blank,
                     int* __restrict__ out_ids, int* __restrict__ out_len)
 {
     __shared__ int warp_cnt[8];
@@ -16,16 +17,17 @@ ctc_collapse_kernel(const long long* __restrict__ ids, int T, int blank,
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long* row = ids + (size_t)b * T;
     int* orow = out_ids + (size_t)b * T;
+    const int Tb = frames ? min(max(frames[b], 0), T) : T;
     if (tid == 0) base_s = 0;
     __syncthreads();
-    for (int t0 = 0; t0 < T; t0 += 256) {
+    for (int t0 = 0; t0 < Tb; t0 += 256) {
         const int t = t0 + tid;
         long long p = blank, prev = blank;
-        if (t < T) {
+        if (t < Tb) {
             p = row[t];
             prev = (t > 0) ? row[t - 1] : (long long)blank;   // `previous` starts as the blank id
         }
-        const bool keep = (t < T) && (p != blank) && (p != prev || prev == blank);
+        const bool keep = (t < Tb) && (p != blank) && (p != prev || prev == blank);
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) warp_cnt[wid] = __popc(m);
         __syncthreads();
@@ -66,9 +68,9 @@ greedy_argmax_kernel(const float* __restrict__ logp, int N, int V, long long* __
     if (lane == 0) ids[row] = (long long)(bi == 0x7fffffff ? 0 : bi);
 }
 
-int launch_ctc_collapse(const long long* ids, int B, int T, int blank, int* out_ids, int* out_len, cudaStream_t st)
+int launch_ctc_collapse(const long long* ids, const int* frames, int B, int T, int blank, int* out_ids, int* out_len, cudaStream_t st)
 {
-    ctc_collapse_kernel<<<B, 256, 0, st>>>(ids, T, blank, out_ids, out_len);
+    ctc_collapse_kernel<<<B, 256, 0, st>>>(ids, frames, T, blank, out_ids, out_len);
     VASR_LAUNCH_OK("ctc_collapse_kernel");
     return VASR_OK;
 }
@@ -85,11 +87,11 @@ extern "C" int vasr_greedy_argmax(const float* log_probs, int N, int V, int64_t*
     return VASR_OK;
 }
 
-extern "C" int vasr_ctc_collapse(const int64_t* ids, int B, int T, int blank,
+extern "C" int vasr_ctc_collapse(const int64_t* ids, const int32_t* frames, int B, int T, int blank,
                                  int32_t* out_ids, int32_t* out_len, void* stream)
 {
     using namespace vasr;
     VASR_REQUIRE(ids && out_ids && out_len, "vasr_ctc_collapse: null argument");
     VASR_REQUIRE(B > 0 && T > 0, "vasr_ctc_collapse: B and T must be positive (got %d, %d)", B, T);
-    return launch_ctc_collapse((const long long*)ids, B, T, blank, out_ids, out_len, (cudaStream_t)stream);
+    return launch_ctc_collapse((const long long*)ids, frames, B, T, blank, out_ids, out_len, (cudaStream_t)stream);
 }

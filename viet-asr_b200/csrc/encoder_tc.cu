@@ -186,6 +186,7 @@ struct Params {
     long long out_bstride;
     const int* len_out;      // [B]
     int* tile_counter;       // dynamic tile scheduler (zeroed before the launch)
+    int* status;             // range guard: bit 0 is set when a depthwise output does not fit fp16 (zeroed per forward)
     int Cin, Cres, Cout, T_out, pad;
     int n_main, n_res;       // chunks of 32 input channels
     int nN;                  // 256-column (output channel) N blocks per tile (1 or 2)
@@ -588,6 +589,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         constexpr int XP = KC / 2;                               // float2 per window row
         const int cp = lane & 15;
         const int tw = (warp * 2 + (lane >> 4)) * R;
+        float amax = 0.f;
         int gc = 0;
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
@@ -642,6 +644,9 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int r = 0; r < R; ++r)
                     if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
 
+                // range guard: |x| >= 65520 rounds to inf in fp16 (checked once per thread at the end of the kernel)
+#pragma unroll
+                for (int r = 0; r < R; ++r) amax = fmaxf(amax, fmaxf(fabsf(acc[r].x), fabsf(acc[r].y)));
                 PROF_ADD(1);
                 mbar_wait(empty_b + sb, ((gc / BSTAGES) & 1) ^ 1);
                 PROF_ADD(2);
@@ -668,6 +673,7 @@ subblock_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 PROF_ADD(3);
             }
         }
+        if (amax >= 65520.f) atomicOr(p.status, 1);          // a depthwise output left the fp16 range (see vasr_encoder_check)
     }
 #ifdef VASR_DEV
     if (p.prof && lane == 0) {
@@ -715,6 +721,7 @@ struct SegParams {
     const LayerDesc* layers;
     int n_layers;
     int* tile_counter;       // zeroed before the launch
+    int* status;             // range guard: bit 0 is set when a depthwise output does not fit fp16 (zeroed per forward)
     int* done;               // [n_layers][done_stride] completion counters (zeroed): 2 * n_tt per finished (layer, utterance)
     int done_stride;
     int T_out, nN;
@@ -1052,6 +1059,7 @@ segment_kernel(const SegParams p)
         const int cp = lane & 15;
         const int tw = (wg * 2 + (lane >> 4)) * R;
         int sx = 0, sb = 0; uint32_t xph = 0, bph = 0;
+        float amax = 0.f;
         int gc = 0;                                         // running chunk index over all tiles (both groups count all)
         for (int ti = 0;; ++ti) {
             const int tile = next_tile(ti);
@@ -1080,6 +1088,9 @@ segment_kernel(const SegParams p)
                     for (int r = 0; r < R; ++r)
                         if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
                 }
+                // range guard: |x| >= 65520 rounds to inf in fp16 (checked once per thread at the end of the kernel)
+#pragma unroll
+                for (int r = 0; r < R; ++r) amax = fmaxf(amax, fmaxf(fabsf(acc[r].x), fabsf(acc[r].y)));
                 PROF_ADD(1);
                 mbar_wait(empty_b + sb, bph ^ 1);
                 PROF_ADD(2);
@@ -1109,6 +1120,7 @@ segment_kernel(const SegParams p)
                 PROF_ADD(3);
             }
         }
+        if (amax >= 65520.f) atomicOr(p.status, 1);          // a depthwise output left the fp16 range (see vasr_encoder_check)
     }
 #ifdef VASR_DEV
     if (p.prof && lane == 0) {
@@ -1500,6 +1512,7 @@ segment_pair_kernel(const SegParams p)
         const int tw = (wg * 2 + (lane >> 4)) * R;
         const uint32_t full_b_leader = mapa_u32(full_b, 0);
         int sx = 0, sb = 0; uint32_t xph = 0, bph = 0;
+        float amax = 0.f;
         int gc = 0;                                         // running chunk index over all tiles (both groups count all)
         for (int item = item0; item < n_items; item += item_step) {
             int l, b, t0; bool dup;
@@ -1531,6 +1544,9 @@ segment_pair_kernel(const SegParams p)
                     for (int r = 0; r < R; ++r)
                         if (t0 + tw + r >= len_mid) acc[r] = make_float2(0.f, 0.f);
                 }
+                // range guard: |x| >= 65520 rounds to inf in fp16 (checked once per thread at the end of the kernel)
+#pragma unroll
+                for (int r = 0; r < R; ++r) amax = fmaxf(amax, fmaxf(fabsf(acc[r].x), fabsf(acc[r].y)));
                 PROF_ADD(1);
                 mbar_wait(empty_b + sb, bph ^ 1);                  // multicast commit of the leader's MMA thread
                 PROF_ADD(2);
@@ -1562,6 +1578,7 @@ segment_pair_kernel(const SegParams p)
                 PROF_ADD(3);
             }
         }
+        if (amax >= 65520.f) atomicOr(p.status, 1);          // a depthwise output left the fp16 range (see vasr_encoder_check)
     }
 #ifdef VASR_DEV
     if (p.prof && lane == 0) {
@@ -1834,7 +1851,7 @@ static void dev_prof_print(const char* head, const unsigned long long* d, cudaSt
 int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const float* res_in, long long r_bstride,
                        float* y, long long y_bstride, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
-                       int* tile_counter, int grid_limit, cudaStream_t st)
+                       int* tile_counter, int* status, int grid_limit, cudaStream_t st)
 {
     using namespace tc;
     (void)len_in;
@@ -1877,7 +1894,7 @@ int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const 
             sb.tmc_r = res_in; sb.tmc_rs = r_bstride;
         }
     }
-    p.tile_counter = tile_counter;
+    p.tile_counter = tile_counter; p.status = status;
     p.n_tt = ceil_div(T_out, TN); p.n_utt = nb; p.n_cg = sb.cout / co_cta;
     const int n_tiles = p.n_tt * p.n_utt * p.n_cg;
     if (sb.tmc_y != y || sb.tmc_yB != B || sb.tmc_yT != T_out || sb.tmc_ys != y_bstride) {
@@ -2001,7 +2018,7 @@ bool segment_tc_ok(const SegLayer* L, int n, int split3)
 }
 
 int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0, int nb,
-                      int* tile_counter, int* done, int done_stride, int grid_limit, cudaStream_t st)
+                      int* tile_counter, int* status, int* done, int done_stride, int grid_limit, cudaStream_t st)
 {
     using namespace tc;
     if (!segment_tc_ok(L, n, split3)) return set_error(VASR_EINVAL, "tcgen05 path: layers do not form a segment");
@@ -2062,7 +2079,7 @@ int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0
         g_seg_cache.push_back(SegCacheEntry{key, B, T, variant, d_desc});
     }
     p.layers = d_desc; p.n_layers = n;
-    p.tile_counter = tile_counter; p.done = done; p.done_stride = done_stride;
+    p.tile_counter = tile_counter; p.status = status; p.done = done; p.done_stride = done_stride;
     p.T_out = T; p.b0 = b0; p.n_tt = ceil_div(T, tr); p.n_utt = nb;
     const long long tpl = (long long)p.n_tt * p.n_utt;
     const long long n_items = (pair ? (tpl + 1) / 2 : tpl) * n;         // work items: tiles, or pairs of tiles

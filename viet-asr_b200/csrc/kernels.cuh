@@ -19,14 +19,14 @@ int launch_pw_gemm(const float* X, const float* W, int Cin, const float* R, cons
 int launch_decoder(const float* enc, const float* W, const float* bias, int Cin, int V1,
                    int N, float* logp, long long* ids, cudaStream_t st);
 
-int launch_ctc_collapse(const long long* ids, int B, int T, int blank, int* out_ids, int* out_len,
+int launch_ctc_collapse(const long long* ids, const int* frames, int B, int T, int blank, int* out_ids, int* out_len,
                         cudaStream_t st);
 
 // tcgen05 fused sub-block (encoder_tc.cu); returns VASR_EINVAL when the shape is not built
 int launch_subblock_tc(SubBlock& sb, const float* x, long long x_bstride, const float* res_in, long long r_bstride,
                        float* y, long long y_bstride, int B, int T_in,
                        int T_out, const int* len_in, const int* len_out, int split3, int b0, int nb,
-                       int* tile_counter, int grid_limit, cudaStream_t st);
+                       int* tile_counter, int* status, int grid_limit, cudaStream_t st);
 bool subblock_tc_supported(const SubBlock& sb);
 // multi-layer persistent launch over a run of stride-1 separable sub-blocks with the same cout and frame count
 struct SegLayer {
@@ -39,7 +39,7 @@ struct SegLayer {
 bool segment_tc_layer_ok(const SubBlock& sb);
 bool segment_tc_ok(const SegLayer* L, int n, int split3);
 int launch_segment_tc(const SegLayer* L, int n, int B, int T, int split3, int b0, int nb,
-                      int* tile_counter, int* done, int done_stride, int grid_limit, cudaStream_t st);
+                      int* tile_counter, int* status, int* done, int done_stride, int grid_limit, cudaStream_t st);
 int tc_init();
 // w_main [cout][cin], w_res [cout][res_cin] (or null): BN-scale-folded fp32 weights on the host
 int tc_prepare_layer(SubBlock& sb, const float* w_main, const float* w_res, const float* dw_kc /*[K][cin] or null*/,

@@ -69,18 +69,27 @@ class VietASR:
         self.encoder.set_gemm_mode(mode)
 
     # ---- device route (module by module)
+    def utterance_frames(self, length: torch.Tensor) -> torch.Tensor:
+        """Encoder frames every utterance of a zero-padded batch would have on its own: T_f = 1 + L // hop
+        (features.py:245-301 with pad_to = 0), then the encoder's stride arithmetic.  The decoders run each utterance
+        over exactly these frames, so a transcript does not depend on what else is in the batch."""
+        return self.encoder.out_frames_of(torch.div(length.to(torch.int64), self.preprocessor.hop_length, rounding_mode="floor") + 1)
+
     @torch.no_grad()
     def forward_device(self, wave: torch.Tensor, length: torch.Tensor, want_log_probs: bool = False):
         feat, seq = self.preprocessor.forward_channels_last(wave, length)
         enc, enc_len = self.encoder.forward_channels_last(feat, seq)
         logp, ids = self.decoder.forward_channels_last(enc, want_log_probs)
-        out_ids, out_len = asr.ctc_collapse(ids, len(self.labels))
+        frames = self.utterance_frames(length)
+        out_ids, out_len = asr.ctc_collapse(ids, len(self.labels), frames=frames)
         return {"feat": feat, "seq": seq, "enc": enc, "enc_len": enc_len, "log_probs": logp, "ids": ids,
-                "out_ids": out_ids, "out_len": out_len}
+                "out_ids": out_ids, "out_len": out_len, "frames": frames}
 
     def transcribe_batch_device(self, wave: torch.Tensor, length: torch.Tensor) -> List[str]:
         r = self.forward_device(wave, length)
-        return asr.ids_to_text(r["out_ids"], r["out_len"], self.labels)
+        texts = asr.ids_to_text(r["out_ids"], r["out_len"], self.labels)      # (device -> host: synchronises)
+        self.encoder.check_range(wave.shape[0])
+        return texts
 
     # ---- host route (one C-ABI call, host buffers)
     def out_frames(self, L: int) -> int:
@@ -112,7 +121,9 @@ class VietASR:
         feat, seq = self.preprocessor.forward_channels_last(wave, length)
         enc, _ = self.encoder.forward_channels_last(feat, seq)
         logp, _ = self.decoder.forward_channels_last(enc, True)
-        return self.beam.decode_batch(logp)
+        texts = self.beam.decode_batch(logp, frames=self.utterance_frames(length))
+        self.encoder.check_range(wave.shape[0])
+        return texts
 
     def transcribe_batch(self, signals: Sequence[np.ndarray], decoder: Optional[str] = None) -> List[str]:
         """List of 1-D float waveforms (16 kHz) -> transcripts; zero-pads to the longest
