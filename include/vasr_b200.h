@@ -243,6 +243,16 @@ int  vasr_resample(vasr_resampler* rs, const void* x, int pcm16, const int64_t* 
 int  vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const float* wave_host,
                           const int64_t* length_host, int B, int64_t L,
                           int32_t* out_ids_host, int32_t* out_len_host, void* stream);
+/* Same, but the collapsed ids stay in caller-owned DEVICE buffers out_ids_dev [B, T_e] / out_len_dev [B] and nothing is
+ * synchronised: the pipelined host->device copy of the waveforms and the compute are enqueued on `stream` (and the
+ * handle's helper streams, joined back into it).  For data-parallel runs: every rank feeds its own host shard and the
+ * ids are gathered over NCCL (replaces the .cpu()/all_gather of the reference's PtActions._infer,
+ * nemo/backends/pytorch/actions.py:594-612, 784-811).  vasr_transcribe_check synchronises `stream` and reports the
+ * range guard (VASR_ERANGE) of the last such call. */
+int  vasr_transcribe_host_to_device(vasr_frontend* fe, vasr_model* m, const float* wave_host,
+                                    const int64_t* length_host, int B, int64_t L,
+                                    int32_t* out_ids_dev, int32_t* out_len_dev, void* stream);
+int  vasr_transcribe_check(vasr_model* m, void* stream);
 
 #ifdef __cplusplus
 }

@@ -490,7 +490,7 @@ def test_device_lm_scores_match_oracle_tiny(order):
     _check_device_lm(V, tiny_lm_path(order), V.configs.EN_LABELS, 300)
 
 
-@pytest.mark.parametrize("name", ["3-gram-lm.binary", "5-gram-lm.binary"])
+@pytest.mark.parametrize("name", ["3-gram-lm.binary", "4-gram-lm.binary", "5-gram-lm.binary"])
 def test_device_lm_scores_match_oracle_shipped(name):
     V = _cuda()
     from conftest import shipped_lm_path
@@ -538,7 +538,8 @@ def test_beam_search_lm_degenerates_to_no_lm():
     assert torch.allclose(a[2], b[2], atol=1e-4)
 
 
-@pytest.mark.parametrize("name,beam_width", [("3-gram-lm.binary", 20), ("3-gram-lm.binary", 100), ("5-gram-lm.binary", 100)])
+@pytest.mark.parametrize("name,beam_width", [("3-gram-lm.binary", 20), ("3-gram-lm.binary", 100), ("4-gram-lm.binary", 50),
+                                             ("5-gram-lm.binary", 100)])
 def test_beam_search_lm_matches_oracle_on_real_speech(name, beam_width):
     """The reference's default decode (infer.py:184-191: 3-gram LM, beam 100, alpha 0.5, beta 1.5) on the
     reference-generated posteriors of real Vietnamese speech."""
@@ -670,3 +671,61 @@ def test_range_guard_reports_fp16_overflow():
             bad.transcribe_batch_device(w80.cuda(), torch.full((B,), 32000))
     fp = _engine(V, md, big, dec_sd, "fp32")
     fp.transcribe_batch_device(wave.cuda(), length.cuda())
+
+
+# ----------------------------------------------------------------------------- round-2 golden sets
+def clips_b48():
+    """The 48 five-second clips of tests/golden/en15x5_real_b48.npz, rebuilt from its recipe and the speech stored in
+    vi12x1_real_all.npz (oracle/make_golden_r2.py clip_from)."""
+    g, a = load_golden("en15x5_real_b48"), load_golden("vi12x1_real_all")
+    L = int(g["L"])
+    clips = []
+    for s_, o in zip(g["src"], g["off"]):
+        x = np.roll(a["pcm16"][s_, : int(a["lens"][s_])], -int(o))
+        clips.append(np.tile(x, -(-L // len(x)))[:L])
+    return np.stack(clips), g
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_every_sample_wav_alone_matches_reference(mode):
+    """All 7 native-16 kHz sample WAVs of the reference + test1.wav (8 kHz, resampled on the host), each transcribed
+    ALONE like infer.py:167-171: greedy ids bit-exact, log-probs within 1e-3, transcript equal."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "real")
+    g = load_golden("vi12x1_real_all")
+    eng = _engine(V, md, enc_sd, dec_sd, mode)
+    for i in range(len(g["lens"])):
+        n, f = int(g["lens"][i]), int(g["frames"][i])
+        wave = pcm_to_wave(g["pcm16"][i:i + 1, :n]).cuda()
+        r = eng.forward_device(wave, torch.tensor([n]).cuda(), want_log_probs=True)
+        assert r["ids"].shape[1] == f
+        ref_logp = torch.from_numpy(g["logits"][i, :f]).log_softmax(-1)
+        rel = ((r["log_probs"][0].cpu() - ref_logp).norm() / ref_logp.norm()).item()
+        assert rel < LOGIT_REL, (str(g["names"][i]), rel)
+        assert torch.equal(r["ids"][0].cpu(), torch.from_numpy(g["ids"][i, :f].astype(np.int64))), str(g["names"][i])
+        assert V.ids_to_text(r["out_ids"], r["out_len"], md["labels"]) == [str(g["texts"][i])]
+        assert eng.transcribe_batch([wave[0].cpu().numpy()], decoder="greedy") == [str(g["texts"][i])]   # host route
+
+
+def test_benchmark_shape_batch_matches_reference():
+    """BASELINE configs[2] shape with real speech: 48 x 5 s through the shipped 15x5 checkpoint - large enough for the
+    128-row CTA-pair kernel (the bench path; small batches use 32-row tiles) - against ids and logits generated by the
+    reference's own code (oracle/make_golden_r2.py)."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("en15x5", "real")
+    clips, g = clips_b48()
+    eng = _engine(V, md, enc_sd, dec_sd, "f16x3")
+    wave = pcm_to_wave(clips).cuda()
+    length = torch.full((len(clips),), clips.shape[1], dtype=torch.int64).cuda()
+    r = eng.forward_device(wave, length, want_log_probs=True)
+    ref_ids = torch.from_numpy(g["ids"].astype(np.int64))
+    assert torch.equal(r["ids"].cpu(), ref_ids), f"{(r['ids'].cpu() != ref_ids).sum().item()} frames differ"
+    ref_logp = torch.from_numpy(g["logits4"]).log_softmax(-1)
+    rel = ((r["log_probs"][:4].cpu() - ref_logp).norm() / ref_logp.norm()).item()
+    assert rel < LOGIT_REL, rel
+    assert V.ids_to_text(r["out_ids"], r["out_len"], md["labels"]) == [str(t) for t in g["texts"]]
+    # the same clips replicated to the benchmark's batch of 256 (both sub-batch streams, every SM busy): identical rows
+    big = eng.forward_device(wave.repeat(6, 1)[:256], length.repeat(6)[:256])
+    assert torch.equal(big["ids"][:48], r["ids"]) and torch.equal(big["ids"][240:256], r["ids"][:16])
+    ids_h, len_h = eng.transcribe_host_ids(pcm_to_wave(clips).pin_memory(), length.cpu().pin_memory())
+    assert torch.equal(ids_h, r["out_ids"].cpu()) and torch.equal(len_h, r["out_len"].cpu())

@@ -204,3 +204,33 @@ def test_c_restatement_of_argmax_and_collapse():
     assert CO.greedy_argmax(tie).tolist() == [[0, 2, 3]] == torch.from_numpy(tie).argmax(-1).tolist()
     out, n = CO.ctc_collapse(np.array([[3, 3, 3, 3], [0, 0, 1, 1], [0, 3, 0, 0], [3, 1, 3, 1]]), 3)
     assert n.tolist() == [0, 2, 2, 2] and out[1, :2].tolist() == [0, 1] and out[2, :2].tolist() == [0, 0]
+
+
+def test_oracle_matches_round2_goldens():
+    """oracle/make_golden_r2.py fixtures (outputs of the reference's own parts/jasper.py): the restatement reproduces
+    the reference ids on a sample transcribed alone (vi 12x1) and on two clips of the benchmark-shaped 15x5 batch."""
+    from conftest import have_weights, load_weights
+    import viet_asr_b200 as V
+    if not have_weights("vi12x1") or not have_weights("en15x5"):
+        pytest.skip("shipped checkpoints not present")
+    g = load_golden("vi12x1_real_all")
+    md = V.configs.quartznet12x1_vi()
+    enc_sd, dec_sd = load_weights("vi12x1")
+    i = 5                                                   # the shortest sample (2.4 s)
+    n, f = int(g["lens"][i]), int(g["frames"][i])
+    r = O.full_path(enc_sd, dec_sd, md["JasperEncoder"]["jasper"], pcm_to_wave(g["pcm16"][i:i + 1, :n]), torch.tensor([n]))
+    assert r["ids"].shape[1] == f == O.utterance_frames(md["JasperEncoder"]["jasper"], [n])[0]
+    assert np.array_equal(r["ids"][0].numpy(), g["ids"][i, :f])
+    assert O.ids_to_text(O.ctc_collapse(r["ids"].numpy(), len(md["labels"])), md["labels"]) == [str(g["texts"][i])]
+    b = load_golden("en15x5_real_b48")
+    md = V.configs.quartznet15x5()
+    enc_sd, dec_sd = load_weights("en15x5")
+    L = int(b["L"])
+    clips = []
+    for s_, o in list(zip(b["src"], b["off"]))[:2]:
+        x = np.roll(g["pcm16"][s_, : int(g["lens"][s_])], -int(o))
+        clips.append(np.tile(x, -(-L // len(x)))[:L])
+    r = O.full_path(enc_sd, dec_sd, md["JasperEncoder"]["jasper"], pcm_to_wave(np.stack(clips)), torch.full((2,), L))
+    assert np.array_equal(r["ids"].numpy(), b["ids"][:2].astype(np.int64))
+    ref_logp = torch.from_numpy(b["logits4"][:2]).log_softmax(-1)
+    assert (r["logp"] - ref_logp).abs().max().item() < 2e-4

@@ -81,6 +81,8 @@ PROTOTYPES = {
     "vasr_pcm16_to_float": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "vasr_resample": (_i, [_vp, _vp, _i, _vp, _i, _i64, _i, _i, _vp, _vp, _i64, _vp]),
     "vasr_transcribe_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "vasr_transcribe_host_to_device": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "vasr_transcribe_check": (_i, [_vp, _vp]),
 }
 
 _lib = None

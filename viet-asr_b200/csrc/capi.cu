@@ -60,6 +60,7 @@ struct vasr_model {
     int max_sub = 2;   // measured on B200: 2 sub-batches beat 1 (tail overlap) and 4 (weight re-streaming)
     // scratch of vasr_transcribe_host (grown on demand)
     void* scratch = nullptr; size_t scratch_bytes = 0;
+    size_t last_ws_off = 0, last_ws_bytes = 0; int last_B = 0;   // encoder workspace of the last vasr_transcribe_host_to_device
 };
 
 namespace vasr {
@@ -547,12 +548,15 @@ extern "C" int vasr_decoder_forward(vasr_model* m, const float* enc, int B, int 
                           (long long*)ids, (cudaStream_t)stream);
 }
 
-extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const float* wave_host,
-                                    const int64_t* length_host, int B, int64_t L,
-                                    int32_t* out_ids_host, int32_t* out_len_host, void* stream)
+// whole path from HOST waveforms; results either copied back to host buffers (then the call synchronises and checks the
+// range guard) or left in caller-owned DEVICE buffers (everything stays enqueued on `stream`)
+static int transcribe_impl(vasr_frontend* fe, vasr_model* m, const float* wave_host,
+                           const int64_t* length_host, int B, int64_t L,
+                           int32_t* out_ids, int32_t* out_len, bool out_on_host, void* stream)
 {
     using namespace vasr;
-    VASR_REQUIRE(fe && m && wave_host && length_host && out_ids_host && out_len_host, "vasr_transcribe_host: null argument");
+    int32_t* out_ids_host = out_ids; int32_t* out_len_host = out_len;
+    VASR_REQUIRE(fe && m && wave_host && length_host && out_ids && out_len, "vasr_transcribe_host: null argument");
     if (!m->finalized) return set_error(VASR_ESTATE, "vasr_transcribe_host: weights not finalized");
     if (m->blocks.empty() || !m->d_dec_w) return set_error(VASR_ESTATE, "vasr_transcribe_host: needs a handle with encoder and decoder");
     VASR_REQUIRE(B > 0, "vasr_transcribe_host: batch must be positive");
@@ -641,6 +645,14 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
     VASR_CUDA_OK(cudaMemcpyAsync(s + o_frames, frames.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if ((rc = vasr_ctc_collapse((const int64_t*)(s + o_ids), (const int32_t*)(s + o_frames), B, T_e, m->num_classes - 1,
                                 (int32_t*)(s + o_oid), (int32_t*)(s + o_olen), st))) return rc;
+    if (!out_on_host) {
+        // results stay on the device (e.g. for an NCCL gather); nothing is synchronised - the caller checks the range
+        // guard with vasr_transcribe_check once it has synchronised anyway
+        VASR_CUDA_OK(cudaMemcpyAsync(out_ids, s + o_oid, (size_t)B * T_e * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        VASR_CUDA_OK(cudaMemcpyAsync(out_len, s + o_olen, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        m->last_ws_off = o_ws; m->last_ws_bytes = ws_b; m->last_B = B;
+        return VASR_OK;
+    }
     VASR_CUDA_OK(cudaMemcpyAsync(out_ids_host, s + o_oid, (size_t)B * T_e * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VASR_CUDA_OK(cudaMemcpyAsync(out_len_host, s + o_olen, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     VASR_CUDA_OK(cudaStreamSynchronize(st));
@@ -662,4 +674,26 @@ extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const floa
     }
 #endif
     return VASR_OK;
+}
+
+extern "C" int vasr_transcribe_host(vasr_frontend* fe, vasr_model* m, const float* wave_host,
+                                    const int64_t* length_host, int B, int64_t L,
+                                    int32_t* out_ids_host, int32_t* out_len_host, void* stream)
+{
+    return transcribe_impl(fe, m, wave_host, length_host, B, L, out_ids_host, out_len_host, true, stream);
+}
+
+extern "C" int vasr_transcribe_host_to_device(vasr_frontend* fe, vasr_model* m, const float* wave_host,
+                                              const int64_t* length_host, int B, int64_t L,
+                                              int32_t* out_ids_dev, int32_t* out_len_dev, void* stream)
+{
+    return transcribe_impl(fe, m, wave_host, length_host, B, L, out_ids_dev, out_len_dev, false, stream);
+}
+
+extern "C" int vasr_transcribe_check(vasr_model* m, void* stream)
+{
+    using namespace vasr;
+    VASR_REQUIRE(m, "vasr_transcribe_check: null model");
+    if (!m->scratch || m->last_B <= 0) { VASR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream)); return VASR_OK; }
+    return vasr_encoder_check(m, (char*)m->scratch + m->last_ws_off, m->last_ws_bytes, m->last_B, stream);
 }

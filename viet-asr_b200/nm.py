@@ -326,3 +326,20 @@ class DataLayerNM(NeuralModule):
 
     @property
     def num_weights(self): return 0
+
+
+# ----------------------------------------------------------------------------- reference backend
+# Inside the reference tree the drop-in modules subclass the reference's OWN base classes (INTEGRATION.md section 1:
+# "change one import line in asr.py").  VASR_NM_BACKEND=nemo does exactly that without editing a file: every name
+# asr.py / pipeline.py import from this module is re-bound to the class of the same name in the vendored NeMo 0.10
+# (`nemo` must be importable).  tests/test_boundary_reference.py runs infer.py's wiring this way against
+# /root/reference.
+import os as _os
+
+if _os.environ.get("VASR_NM_BACKEND") == "nemo":
+    from nemo.backends.pytorch.nm import DataLayerNM, NonTrainableNM, TrainableNM      # noqa: F401,E402
+    from nemo.core import DeviceType, NeuralModule, NeuralModuleFactory                  # noqa: F401,E402
+    from nemo.core.neural_types import (AcousticEncodedRepresentation, AudioSignal, ChannelType, LengthsType,  # noqa: F401,E402
+                                        LogprobsType, MelSpectrogramType, NeuralPortNameMismatchError,
+                                        NeuralPortNmTensorMismatchError, NeuralType, NeuralTypeError, NmTensor,
+                                        PredictionsType, SpectrogramType, VoidType)

@@ -114,6 +114,32 @@ class VietASR:
                                               torch.cuda.current_stream().cuda_stream))
         return out_ids, out_len
 
+    def transcribe_host_to_device(self, wave_host: torch.Tensor, length_host: torch.Tensor,
+                                  out_ids: Optional[torch.Tensor] = None, out_len: Optional[torch.Tensor] = None):
+        """Host waveforms in (pinned for asynchronous copies), collapsed ids left on the DEVICE, nothing synchronised:
+        the copy / compute pipeline of `transcribe_host_ids` for callers that hand the result to a collective
+        (`dist.gather_results`).  `check_range()` afterwards reports an fp16 overflow of the tensor-core modes."""
+        if wave_host.is_cuda or length_host.is_cuda:
+            raise ValueError("transcribe_host_to_device takes host tensors")
+        w = wave_host.to(torch.float32).contiguous()
+        ln = length_host.to(torch.int64).contiguous()
+        B, L = w.shape
+        T_e = self.out_frames(L)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if out_ids is None:
+            out_ids = torch.empty((B, T_e), dtype=torch.int32, device=dev)
+        if out_len is None:
+            out_len = torch.empty((B,), dtype=torch.int32, device=dev)
+        h = self.encoder._sync_weights()
+        _lib.check(h.lib.vasr_transcribe_host_to_device(self.preprocessor._h, h.h, w.data_ptr(), ln.data_ptr(), B, L,
+                                                        out_ids.data_ptr(), out_len.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream))
+        return out_ids, out_len
+
+    def check_range(self):
+        h = self.encoder._sync_weights()
+        _lib.check(h.lib.vasr_transcribe_check(h.h, torch.cuda.current_stream().cuda_stream))
+
     @torch.no_grad()
     def beam_batch_device(self, wave: torch.Tensor, length: torch.Tensor) -> List[str]:
         """Device tensors -> transcripts through the beam-search decoder (with the n-gram LM when the engine was
