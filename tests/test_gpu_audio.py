@@ -154,3 +154,33 @@ def test_oracle_resampled_input_gives_same_log_probs():
     a = eng.forward_device(y, n, want_log_probs=True)["log_probs"]
     b = eng.forward_device(want.cuda(), n, want_log_probs=True)["log_probs"]
     assert ((a - b).norm() / b.norm()).item() < 1e-3
+
+
+def test_wer_over_a_manifest(tmp_path):
+    """WER / CER over a NeMo-format manifest next to the throughput.  The manifest holds the reference's
+    sample utterances (written out as WAV files) with the REFERENCE's own greedy transcripts as text
+    (tests/golden/vi12x1_real_all.npz, oracle/make_golden_r2.py): the B200 path, run one utterance per batch like
+    infer.py, must score WER = CER = 0 against them; batched with padding it may differ in the last frame only."""
+    import json
+    V = _cuda()
+    from conftest import have_weights, load_weights
+    if not have_weights("vi12x1"):
+        pytest.skip("weights/vi12x1 not present")
+    md = V.configs.quartznet12x1_vi()
+    eng = V.VietASR(model_definition=md, gemm_mode="f16x3", decoder="greedy")
+    eng.load_state_dicts(*load_weights("vi12x1"))
+    g = load_golden("vi12x1_real_all")
+    man = tmp_path / "manifest.json"
+    with open(man, "w", encoding="utf-8") as f:
+        for i, n in enumerate(g["lens"]):
+            p = tmp_path / f"utt{i}.wav"
+            _write_wav16(p, g["pcm16"][i, : int(n)], 16000)
+            f.write(json.dumps({"audio_filepath": p.name, "duration": int(n) / 16000.0, "text": str(g["texts"][i])}, ensure_ascii=False) + "\n")
+    alone = V.evaluate_manifest(eng, str(man), batch_size=1)
+    assert alone["utterances"] == 8 and alone["wer"] == 0.0 and alone["cer"] == 0.0, alone
+    batched = V.evaluate_manifest(eng, str(man), batch_size=8)
+    assert batched["wer"] < 0.03 and batched["audio_s_per_s"] > 0
+    with open(man, "a", encoding="utf-8") as f:
+        f.write(json.dumps({"audio_filepath": "x.wav", "text": "a"}) + "\n")
+    with pytest.raises(ValueError, match="without proper duration key"):
+        list(V.read_manifest(str(man)))

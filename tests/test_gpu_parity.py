@@ -729,3 +729,25 @@ def test_benchmark_shape_batch_matches_reference():
     assert torch.equal(big["ids"][:48], r["ids"]) and torch.equal(big["ids"][240:256], r["ids"][:16])
     ids_h, len_h = eng.transcribe_host_ids(pcm_to_wave(clips).pin_memory(), length.cpu().pin_memory())
     assert torch.equal(ids_h, r["out_ids"].cpu()) and torch.equal(len_h, r["out_len"].cpu())
+
+
+def test_cuda_graph_route_equals_call_route():
+    """the fixed-shape greedy path captured once as a CUDA graph (VietASR.capture_graph) and replayed
+    with new waveforms and lengths gives exactly the ids of the per-call host route."""
+    V = _cuda()
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "rand")
+    eng = _engine(V, md, enc_sd, dec_sd, "f16x3")
+    g = torch.Generator().manual_seed(31)
+    for B, L in ((1, 80000), (4, 48000)):
+        gr = eng.capture_graph(B, L)
+        assert eng.capture_graph(B, L) is gr                      # cached per shape
+        for rep in range(3):
+            wave = (0.1 * torch.randn(B, L, generator=g)).clamp_(-1, 1)
+            length = torch.full((B,), L, dtype=torch.int64)
+            if rep and B > 1:
+                length[1] = L - 160 * 37 * rep; wave[1, int(length[1]):] = 0
+            ids_g, len_g = gr(wave.pin_memory(), length.pin_memory())
+            ids_h, len_h = eng.transcribe_host_ids(wave.pin_memory(), length.pin_memory())
+            assert torch.equal(ids_g, ids_h) and torch.equal(len_g, len_h), (B, rep)
+    with pytest.raises(ValueError):
+        gr(torch.zeros(2, 100).pin_memory(), torch.tensor([100, 100]).pin_memory())

@@ -24,6 +24,74 @@ from . import _lib, asr, audio, configs
 from .nm import DeviceType, NeuralModuleFactory
 
 
+class GraphedGreedyPath:
+    """The fixed-shape greedy path (front end -> encoder -> decoder -> collapse) for batches of exactly [B, L], captured
+    ONCE as a CUDA graph and replayed per call.  The reference re-sorts the module DAG and
+    re-applies `.eval()` on every `infer` call (nemo/backends/pytorch/actions.py:1437, 414); here the call chain is
+    resolved at capture time - static device buffers, cached tensor maps and descriptor tables, the library's kernels
+    recorded in launch order - so a call is: H2D of the waveform, one graph launch, D2H of the collapsed ids."""
+
+    def __init__(self, eng: "VietASR", B: int, L: int):
+        import ctypes
+        self.eng, self.B, self.L = eng, int(B), int(L)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pre, enc, dec = eng.preprocessor, eng.encoder, eng.decoder
+        h = enc._sync_weights()
+        lib = h.lib
+        T_f = pre.num_frames(self.L)
+        T_e = enc.out_frames(T_f)
+        f32, i64, i32 = torch.float32, torch.int64, torch.int32
+        self.wave = torch.zeros((B, L), dtype=f32, device=dev)
+        self.length = torch.full((B,), L, dtype=i64, device=dev)
+        self.feat = torch.empty((B, T_f, pre.nfilt), dtype=f32, device=dev)
+        self.seq = torch.empty((B,), dtype=i64, device=dev)
+        self.enc = torch.empty((B, T_e, enc._out_ch), dtype=f32, device=dev)
+        self.enc_len = torch.empty((B,), dtype=f32, device=dev)
+        self.ids = torch.empty((B, T_e), dtype=i64, device=dev)
+        self.frames = torch.empty((B,), dtype=i32, device=dev)
+        self.out_ids = torch.empty((B, T_e), dtype=i32, device=dev)
+        self.out_len = torch.empty((B,), dtype=i32, device=dev)
+        self.ws = torch.empty((int(lib.vasr_encoder_workspace_bytes(h.h, B, T_f)),), dtype=torch.uint8, device=dev)
+        self.host_ids = torch.empty((B, T_e), dtype=i32).pin_memory()
+        self.host_len = torch.empty((B,), dtype=i32).pin_memory()
+        blank = len(eng.labels)
+
+        def chain():
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(lib.vasr_frontend_forward(pre._h, self.wave.data_ptr(), self.length.data_ptr(), B, L,
+                                                 self.feat.data_ptr(), self.seq.data_ptr(), st))
+            _lib.check(lib.vasr_encoder_forward(h.h, self.feat.data_ptr(), self.seq.data_ptr(), B, T_f, self.enc.data_ptr(),
+                                                self.enc_len.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
+            _lib.check(lib.vasr_decoder_forward(h.h, self.enc.data_ptr(), B, T_e, None, self.ids.data_ptr(), st))
+            self.frames.copy_(eng.utterance_frames(self.length))
+            _lib.check(lib.vasr_ctc_collapse(self.ids.data_ptr(), self.frames.data_ptr(), B, T_e, blank,
+                                             self.out_ids.data_ptr(), self.out_len.data_ptr(), st))
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up: every cache the chain needs exists before capture
+            chain(); chain()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            chain()
+        self._h, self._lib_ = h, lib
+
+    def __call__(self, wave_host: torch.Tensor, length_host: torch.Tensor):
+        """wave_host [B, L] f32, length_host [B] i64 (pinned host tensors) -> (ids [B, T_e] i32, len [B] i32) pinned."""
+        if tuple(wave_host.shape) != (self.B, self.L):
+            raise ValueError(f"this graph was captured for [{self.B}, {self.L}] waveforms, got {tuple(wave_host.shape)}")
+        self.wave.copy_(wave_host, non_blocking=True)
+        self.length.copy_(length_host, non_blocking=True)
+        self.graph.replay()
+        self.host_ids.copy_(self.out_ids, non_blocking=True)
+        self.host_len.copy_(self.out_len, non_blocking=True)
+        _lib.check(self._lib_.vasr_encoder_check(self._h.h, self.ws.data_ptr(), self.ws.numel(), self.B,
+                                                 torch.cuda.current_stream().cuda_stream))       # synchronises
+        return self.host_ids, self.host_len
+
+
 class VietASR:
     def __init__(self, config_file: Optional[str] = None, encoder_checkpoint: Optional[str] = None,
                  decoder_checkpoint: Optional[str] = None, device: str = "gpu", lm_path: Optional[str] = None,
@@ -90,6 +158,14 @@ class VietASR:
         texts = asr.ids_to_text(r["out_ids"], r["out_len"], self.labels)      # (device -> host: synchronises)
         self.encoder.check_range(wave.shape[0])
         return texts
+
+    def capture_graph(self, B: int, L: int) -> GraphedGreedyPath:
+        """Capture the greedy path for batches of exactly [B, L] samples as a CUDA graph (cached per shape)."""
+        cache = self.__dict__.setdefault("_graphs", {})
+        key = (int(B), int(L), self.encoder._gemm_mode)
+        if key not in cache:
+            cache[key] = GraphedGreedyPath(self, B, L)
+        return cache[key]
 
     # ---- host route (one C-ABI call, host buffers)
     def out_frames(self, L: int) -> int:
