@@ -519,7 +519,12 @@ def main():
         ref, v, med, v_b1, t_b1 = cpu_port_pass(cfg, md, enc_sd, dec_sd, wave_h[:n_par], len_h[:n_par], threads, 2, min(4, n_par))
         ids_equal = bool(torch.equal(f_ids[:n_par].cpu(), ref["ids"]))
         rel = ((f_logp[:n_par].cpu() - ref["logp"]).norm() / ref["logp"].norm()).item()
-        parity = {"clips": n_par, "ids_equal": ids_equal, "logp_rel_l2": rel,
+        t2 = ref["logp"].topk(2, -1).values
+        near_tie = (t2[..., 0] - t2[..., 1]) <= 1e-3               # the reference's own two best classes within the tolerance
+        differ = f_ids[:n_par].cpu() != ref["ids"]
+        parity = {"clips": n_par, "ids_equal": ids_equal, "logp_rel_l2": rel, "frames": int(differ.numel()),
+                  "frames_differing": int(differ.sum()), "frames_differing_outside_near_ties": int((differ & ~near_tie).sum()),
+                  "near_tie_frames": int(near_tie.sum()),
                   "what": f"CPU port of the reference (oracle/quartznet_oracle.py) on the first {n_par} clips of rank 0's GPU batch vs rows "
                           f"[0, {n_par}) of the device leg at batch {B}: greedy ids bit-exact, log-probs rel-L2 (bound 1e-3)"}
         if beam:

@@ -122,10 +122,12 @@ def main():
     off = np.array([(i // 7) * 9973 + 1234 * (i % 5) for i in range(NB)], np.int32)
     clips = np.stack([clip_from(pcms[src[i]], int(off[i]), L) for i in range(NB)])
     lens48 = np.full((NB,), L, np.int64)
-    ids48, logits4 = [], None
+    ids48, logits4, margins = [], None, []
     for s in range(0, NB, 8):
         lg, ids = ref_decode(ref_enc, dec_sd, clips[s:s + 8], lens48[s:s + 8])
         ids48.append(ids)
+        t2 = torch.log_softmax(torch.from_numpy(lg), -1).topk(2, -1).values
+        margins.append((t2[..., 0] - t2[..., 1]).numpy())          # the reference's own top-2 margin of every frame
         if s == 0:
             logits4 = lg[:4]
         print(f"  clips {s}..{s + 7} done")
@@ -133,6 +135,7 @@ def main():
     top = np.sort(torch.log_softmax(torch.from_numpy(logits4), -1).numpy(), axis=-1)
     out = os.path.join(ROOT, "tests/golden/en15x5_real_b48.npz")
     np.savez_compressed(out, src=src, off=off, L=np.int64(L), ids=ids48.astype(np.int8), logits4=logits4,
+                        margin=np.concatenate(margins).astype(np.float16),
                         min_margin4=np.float32((top[..., -1] - top[..., -2]).min()),
                         texts=np.array(O.ids_to_text(O.ctc_collapse(ids48, len(labels)), labels)))
     print("wrote", out, os.path.getsize(out) // 1024, "KiB; first texts:", O.ids_to_text(O.ctc_collapse(ids48[:3], len(labels)), labels))
