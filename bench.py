@@ -66,8 +66,8 @@ def load_peaks():
 
 def load_traffic(mode):
     """dram__bytes_read.sum + dram__bytes_write.sum of the encoder kernels of ONE step from the committed ncu
-    capture (profiles/r1_traffic.json, f16x3, same workload); None for other modes."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    capture (profiles/r2_traffic.json, f16x3, same workload); None for other modes."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if mode != "f16x3" or not os.path.exists(p):
         return None
     d = json.load(open(p))

@@ -372,15 +372,25 @@ class JasperEncoder(TrainableNM):
 
     def out_frames_of(self, feat_frames: torch.Tensor) -> torch.Tensor:
         """Per-utterance T_e for per-utterance feature-frame counts [B] (int tensor, any device): the conv arithmetic
-        of `MaskedConv1d.get_seq_len` (parts/jasper.py:108-111) on integers, block by block."""
-        t = feat_frames.to(torch.int64)
-        for c in self._jasper:
+        of `MaskedConv1d.get_seq_len` (parts/jasper.py:108-111) on integers.  T' = (T + c) // s + 1 with
+        c = 2p - d(k-1) - 1; 'same'-padded stride-1 layers (c = -1) are the identity and are skipped, so QuartzNet
+        costs one integer op per strided block instead of one per sub-block."""
+        steps = self.__dict__.get("_frame_steps")
+        if steps is None:
+            steps = []
             first = lambda v: int(v[0] if isinstance(v, (list, tuple)) else v)
-            k, s_, d = first(c["kernel"]), first(c.get("stride", 1)), first(c.get("dilation", 1))
-            pad = (d * k) // 2 - 1 if d > 1 else k // 2
-            for _ in range(int(c["repeat"])):
-                t = torch.div(t + 2 * pad - d * (k - 1) - 1, s_, rounding_mode="floor") + 1
-        return t.clamp_(min=0).to(torch.int32)
+            for c in self._jasper:
+                k, s_, d = first(c["kernel"]), first(c.get("stride", 1)), first(c.get("dilation", 1))
+                pad = (d * k) // 2 - 1 if d > 1 else k // 2
+                cc = 2 * pad - d * (k - 1) - 1
+                if s_ == 1 and cc == -1:
+                    continue
+                steps += [(cc, s_)] * int(c["repeat"])
+            self.__dict__["_frame_steps"] = steps
+        t = feat_frames.to(torch.int64)
+        for cc, s_ in steps:
+            t = torch.div(t + cc, s_, rounding_mode="floor") + 1
+        return t.clamp(min=0).to(torch.int32)
 
     def check_range(self, B: int):
         """Raise RuntimeError if the last forward on this module overflowed the fp16 operand range of the tensor-core

@@ -1455,14 +1455,20 @@ segment_pair_kernel(const SegParams p)
             if (++ab == nbuf) { ab = 0; accph ^= 1; }
             // finish one 32-column block held in registers: +shift, ReLU, (mask), stage, TMA store
             auto finish = [&](const uint32_t (&rg)[32], int col0) {
+                // the block's BN shift (shared-memory broadcast) is fetched BEFORE the warp synchronises on the staging
+                // buffer: behind the __syncwarp the loads could not be hoisted and every block exposed their latency
+                // (ncu: 23 % of the drain's stall samples sat on the first FFMA2 after these loads)
                 const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                float4 shv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) shv[i] = sh4[i];
                 unsigned char* buf = stage + sbuf * EPI_WARP_BYTES;
                 // the store issued `nbufs` blocks ago has left this buffer
                 if (lane == 0) { if (nbufs == 2) bulk_wait_read<1>(); else if (nbufs == 3) bulk_wait_read<2>(); else bulk_wait_read<3>(); }
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 sh = sh4[i];
+                    const float4 sh = shv[i];
                     float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 0]), __uint_as_float(rg[4 * i + 1])), wsc2, make_float2(sh.x, sh.y));
                     float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 2]), __uint_as_float(rg[4 * i + 3])), wsc2, make_float2(sh.z, sh.w));
                     float4 v = make_float4(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f), fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f));
