@@ -1453,50 +1453,56 @@ segment_pair_kernel(const SegParams p)
             tcgen05_fence_after();
             const int ab_cur = ab;
             if (++ab == nbuf) { ab = 0; accph ^= 1; }
-            // finish one 32-column block held in registers: +shift, ReLU, (mask), stage, TMA store
-            auto finish = [&](const uint32_t (&rg)[32], int col0) {
-                // the block's BN shift (shared-memory broadcast) is fetched BEFORE the warp synchronises on the staging
-                // buffer: behind the __syncwarp the loads could not be hoisted and every block exposed their latency
-                // (ncu: 23 % of the drain's stall samples sat on the first FFMA2 after these loads)
-                const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
-                float4 shv[8];
+            // finish one 32-column block held in registers: +shift, ReLU, (mask), stage, TMA store.  The epilogue is a single
+            // warp per scheduler next to two depthwise warps - its drain time is its instruction count - so tiles that lie
+            // entirely inside the utterance (all but the last one) run without the per-value row mask.
+            auto drain = [&](auto masked_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
+                auto finish = [&](const uint32_t (&rg)[32], int col0) {
+                    // the block's BN shift (shared-memory broadcast) is fetched BEFORE the warp synchronises on the staging
+                    // buffer: behind the __syncwarp the loads could not be hoisted and every block exposed their latency
+                    // (ncu: 23 % of the drain's stall samples sat on the first FFMA2 after these loads)
+                    const float4* sh4 = reinterpret_cast<const float4*>(ep_shift + col0);
+                    float4 shv[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) shv[i] = sh4[i];
-                unsigned char* buf = stage + sbuf * EPI_WARP_BYTES;
-                // the store issued `nbufs` blocks ago has left this buffer
-                if (lane == 0) { if (nbufs == 2) bulk_wait_read<1>(); else if (nbufs == 3) bulk_wait_read<2>(); else bulk_wait_read<3>(); }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 sh = shv[i];
-                    float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 0]), __uint_as_float(rg[4 * i + 1])), wsc2, make_float2(sh.x, sh.y));
-                    float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 2]), __uint_as_float(rg[4 * i + 3])), wsc2, make_float2(sh.z, sh.w));
-                    float4 v = make_float4(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f), fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f));
-                    if (masked && !live) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(buf + row_off + (((uint32_t)i ^ row_sw) << 4)) = v;   // SWIZZLE_128B
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0 && !dup && !DBG_ON(4)) { tma_store_3d(&L->tm_out, buf, col0, t0 + q * 32, b); bulk_commit(); }
-                if (++sbuf == nbufs) sbuf = 0;
-            };
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32b_x32(tbase, ra);
-            tmem_ld_wait();
-#pragma unroll 1
-            for (int blk = 0; blk < nblk; blk += 2) {          // nblk is even
-                tmem_ld_32x32b_x32(tbase + (uint32_t)((blk + 1) * 32), rb);
-                finish(ra, blk * 32);
-                tmem_ld_wait();
-                if (blk + 2 < nblk) tmem_ld_32x32b_x32(tbase + (uint32_t)((blk + 2) * 32), ra);
-                else {                                         // every TMEM read of this tile has completed
-                    tcgen05_fence_before();
+                    for (int i = 0; i < 8; ++i) shv[i] = sh4[i];
+                    unsigned char* buf = stage + sbuf * EPI_WARP_BYTES;
+                    // the store issued `nbufs` blocks ago has left this buffer
+                    if (lane == 0) { if (nbufs == 2) bulk_wait_read<1>(); else if (nbufs == 3) bulk_wait_read<2>(); else bulk_wait_read<3>(); }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * (uint32_t)ab_cur);
-                }
-                finish(rb, (blk + 1) * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sh = shv[i];
+                        float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 0]), __uint_as_float(rg[4 * i + 1])), wsc2, make_float2(sh.x, sh.y));
+                        float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rg[4 * i + 2]), __uint_as_float(rg[4 * i + 3])), wsc2, make_float2(sh.z, sh.w));
+                        float4 v = make_float4(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f), fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f));
+                        if (MASKED && !live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(buf + row_off + (((uint32_t)i ^ row_sw) << 4)) = v;   // SWIZZLE_128B
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !dup && !DBG_ON(4)) { tma_store_3d(&L->tm_out, buf, col0, t0 + q * 32, b); bulk_commit(); }
+                    if (++sbuf == nbufs) sbuf = 0;
+                };
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(tbase, ra);
                 tmem_ld_wait();
-            }
+#pragma unroll 1
+                for (int blk = 0; blk < nblk; blk += 2) {          // nblk is even
+                    tmem_ld_32x32b_x32(tbase + (uint32_t)((blk + 1) * 32), rb);
+                    finish(ra, blk * 32);
+                    tmem_ld_wait();
+                    if (blk + 2 < nblk) tmem_ld_32x32b_x32(tbase + (uint32_t)((blk + 2) * 32), ra);
+                    else {                                         // every TMEM read of this tile has completed
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * (uint32_t)ab_cur);
+                    }
+                    finish(rb, (blk + 1) * 32);
+                    tmem_ld_wait();
+                }
+            };
+            if (masked) drain(std::true_type{}); else drain(std::false_type{});
             if (lane == 0 && !dup) {
                 // this warp's part of the tile is in global memory: publish it to the tiles of the next layer
                 bulk_wait_all0();
