@@ -110,6 +110,13 @@ int64_t     vasr_launch_count(void);
 int  vasr_frontend_create(const vasr_frontend_cfg* cfg, const float* window_host,
                           const float* mel_fb_host, vasr_frontend** out);
 void vasr_frontend_destroy(vasr_frontend* fe);
+/* Where the STFT's centre padding reflects (torch.stft(center=True), features.py:181-188):
+ *   per_utterance = 0 (default): at the end of the batch-padded row of L samples - exactly what the reference computes for
+ *                      a [B, L] tensor; the last feature frame of a SHORTER utterance then sees the zero padding;
+ *   per_utterance = 1: at every utterance's own length[b] - what that utterance sees when the reference transcribes it
+ *                      alone (infer.py:167-171 only ever runs one utterance per call), so a transcript does not depend on
+ *                      what else is in the batch.  Frames at or beyond ceil(length/hop) are zeroed in both modes. */
+int  vasr_frontend_set_padding(vasr_frontend* fe, int per_utterance);
 /* T_f = 1 + L / hop, then padded up to a multiple of pad_to if pad_to > 0 */
 int  vasr_frontend_num_frames(const vasr_frontend* fe, int64_t L);
 /* wave [B, L] f32, length [B] i64  ->  feat [B, T_f, nfilt] f32 (normalised, masked),

@@ -124,9 +124,11 @@ def beam_search_batch(log_probs: np.ndarray, labels: Sequence[str], beam_width: 
 #       score is   lm(text) + alpha * ln(10) * log10 P(next_word | state(text)) [+ unk] + beta   and is never recomputed;
 #   * candidates are pruned at best(combined) + beam_prune_logp and the beam_width best by combined score kept
 #     (stable); beams carry only the acoustic score;
-#   * at the end word_part becomes next_word; a text first seen THEN is scored with is_last_word=True
-#     (+ log10 P(</s> | state)); a text already in the cache keeps its cached score without the </s> term
-#     (the cache is keyed by text only - a quirk of the package, restated as is);
+#   * at the end word_part becomes next_word and EVERY final text is scored with is_last_word=True
+#     (+ log10 P(</s> | state)): pyctcdecode >= 0.5 keys its cache by (text, is_eos), so a text that was already
+#     cached without </s> during the search is scored again (older versions keyed by text only).  A final
+#     text with no pending word gets the </s> term alone here (the package would additionally score an empty word:
+#     not restated - unpinned either way);
 #   * the LM state of a text is the KenLM state after <s> w1 .. wn, i.e. its last order-1 words.
 LOG10_TO_LN = 1.0 / math.log10(math.e)
 AVG_TOKEN_LEN = 6
@@ -152,8 +154,26 @@ def beam_search_lm(log_probs: np.ndarray, labels: Sequence[str], beam_width: int
     # text -> (lm score of the text, KenLM context ids)
     cache = {"": (0.0, [lm.bos])}
 
+    eos_cache = {}                                     # pyctcdecode >= 0.5 keys its cache by (text, is_eos)
+
     def lm_of(text: str, next_word: str, is_eos: bool) -> float:
         new_text = _merge_tokens(text, next_word)
+        if is_eos:
+            # end of the utterance: EVERY final text is scored as the end of the sentence, also one that was already
+            # committed (and cached without </s>) during the search
+            if new_text not in eos_cache:
+                prev, ctx = cache[text]
+                if next_word:
+                    wid = lm.index(next_word)
+                    raw = lm.score(ctx, wid)
+                    if next_word not in lm.word2id:
+                        raw += unk_score_offset
+                    nctx = (ctx + [wid])[-ctx_len:] if ctx_len > 0 else []
+                    raw += lm.score(nctx, lm.eos)
+                    eos_cache[new_text] = prev + alpha * raw * LOG10_TO_LN + beta
+                else:                                   # no pending word: the </s> term alone, no word bonus
+                    eos_cache[new_text] = prev + alpha * lm.score(ctx, lm.eos) * LOG10_TO_LN
+            return eos_cache[new_text]
         if new_text not in cache:
             prev, ctx = cache[text]
             wid = lm.index(next_word)
@@ -161,8 +181,6 @@ def beam_search_lm(log_probs: np.ndarray, labels: Sequence[str], beam_width: int
             if next_word not in lm.word2id:
                 raw += unk_score_offset
             nctx = (ctx + [wid])[-ctx_len:] if ctx_len > 0 else []
-            if is_eos:
-                raw += lm.score(nctx, lm.eos)
             cache[new_text] = (prev + alpha * raw * LOG10_TO_LN + beta, nctx)
         return cache[new_text][0]
 

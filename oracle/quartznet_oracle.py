@@ -308,6 +308,21 @@ def utterance_frames(jasper_cfg: Sequence[dict], length, hop: int = 160) -> List
     return out
 
 
+def filterbank_features_each_alone(x: torch.Tensor, length: torch.Tensor, **kw):
+    """Features of a zero-padded batch computed the way the reference's inference path computes them: one utterance per
+    call (infer.py:167-171), i.e. `filterbank_features` on x[b, :length[b]] alone, then zero-padded to the batch's frame
+    count (frames beyond an utterance's own are masked zeros in the batched tensor anyway, features.py:287-290).  This is
+    what `vasr_frontend_set_padding(fe, 1)` reproduces on the device."""
+    T = x.shape[1] // kw.get("n_window_stride", 160) + 1
+    feats, seqs = [], []
+    for b in range(x.shape[0]):
+        n = int(length[b])
+        f, s = filterbank_features(x[b:b + 1, :n], length[b:b + 1], **kw)
+        feats.append(F.pad(f, (0, T - f.shape[2])))
+        seqs.append(s)
+    return torch.cat(feats), torch.cat(seqs)
+
+
 def ctc_collapse(ids: np.ndarray, blank: int, frames: Optional[Sequence[int]] = None) -> List[List[int]]:
     """helpers.py:20-32: iterate ALL frames of the utterance (no truncation at the encoded length).  `frames`: rows of a
     zero-padded batch are cut to the frames the utterance has on its own (`utterance_frames`) first."""

@@ -762,3 +762,38 @@ def test_cuda_graph_route_equals_call_route():
             assert torch.equal(ids_g, ids_h) and torch.equal(len_g, len_h), (B, rep)
     with pytest.raises(ValueError):
         gr(torch.zeros(2, 100).pin_memory(), torch.tensor([100, 100]).pin_memory())
+
+
+def test_per_utterance_padding_matches_every_utterance_alone():
+    """vasr_frontend_set_padding(fe, 1): batched features equal `filterbank_features` of every utterance ALONE for
+    arbitrary (non-hop-multiple) lengths, and a batch_invariant engine transcribes a ragged batch exactly as it
+    transcribes each utterance alone."""
+    V = _cuda()
+    V.NeuralModuleFactory(placement=V.DeviceType.GPU)
+    lens = [24000, 23999, 17777, 12345, 801]
+    L = max(lens)
+    g = torch.Generator().manual_seed(41)
+    wave = torch.zeros((len(lens), L))
+    for i, n in enumerate(lens):
+        wave[i, :n] = (0.1 * torch.randn(n, generator=g)).clamp_(-1, 1)
+    length = torch.tensor(lens, dtype=torch.int64)
+    pre = V.AudioToMelSpectrogramPreprocessor(**V.configs.PREPROCESSOR_DEFAULT)
+    pre.set_padding(True)
+    feats, seq = pre.forward(input_signal=wave.cuda(), length=length.cuda())
+    ref, ref_seq = O.filterbank_features_each_alone(wave, length)
+    assert seq.cpu().tolist() == ref_seq.tolist()
+    assert (feats.cpu() - ref).abs().max().item() < FEAT_ATOL
+    batched_ref, _ = O.filterbank_features(wave, length)                     # the [B, L] tensor semantics differ ...
+    assert (batched_ref[1:] - ref[1:]).abs().max().item() > 1e-2             # ... in the last frame of shorter utterances
+    md, enc_sd, dec_sd = model_and_weights("vi12x1", "rand")
+    eng = V.VietASR(model_definition=md, gemm_mode="f16x3", decoder="greedy", batch_invariant=True)
+    eng.load_state_dicts(enc_sd, dec_sd)
+    r = eng.forward_device(wave.cuda(), length.cuda())
+    out, n = r["out_ids"].cpu().numpy(), r["out_len"].cpu().numpy()
+    for i, nl in enumerate(lens):
+        one = eng.forward_device(wave[i:i + 1, :nl].cuda(), length[i:i + 1].cuda())
+        f = int(r["frames"][i])
+        assert torch.equal(one["ids"][0], r["ids"][i, :f]), i
+        assert out[i, : n[i]].tolist() == one["out_ids"][0, : int(one["out_len"][0])].cpu().tolist(), i
+    ids_h, len_h = eng.transcribe_host_ids(wave.pin_memory(), length.pin_memory())
+    assert [row[:k].tolist() for row, k in zip(ids_h.numpy(), len_h.numpy())] == [out[i, : n[i]].tolist() for i in range(len(lens))]

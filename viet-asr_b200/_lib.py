@@ -49,6 +49,7 @@ PROTOTYPES = {
     "vasr_launch_count": (_i64, []),
     "vasr_frontend_create": (_i, [C.POINTER(FrontendCfg), _vp, _vp, C.POINTER(_vp)]),
     "vasr_frontend_destroy": (None, [_vp]),
+    "vasr_frontend_set_padding": (_i, [_vp, _i]),
     "vasr_frontend_num_frames": (_i, [_vp, _i64]),
     "vasr_frontend_forward": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
     "vasr_model_create": (_i, [C.POINTER(BlockCfg), _i, _i, _i, C.POINTER(_vp)]),

@@ -177,6 +177,13 @@ class AudioToMelSpectrogramPreprocessor(NonTrainableNM):
             t += self.pad_to - t % self.pad_to
         return t
 
+    def set_padding(self, per_utterance: bool):
+        """False (default): the STFT reflects at the end of the padded batch row, the reference's semantics for a [B, L]
+        tensor.  True: every utterance is reflected at its own length - what it sees when the reference transcribes it
+        alone - so batched features equal the single-utterance ones for every length (vasr_frontend_set_padding)."""
+        _lib.check(self._lib.vasr_frontend_set_padding(self._h, 1 if per_utterance else 0))
+        self.pad_per_utterance = bool(per_utterance)
+
     def forward_channels_last(self, input_signal: torch.Tensor, length: torch.Tensor):
         _require_cuda(input_signal, "AudioToMelSpectrogramPreprocessor")
         x = input_signal.to(torch.float32).contiguous()

@@ -10,9 +10,9 @@
 // LM fusion (template parameter LM): every beam also carries the LM score of its committed text, the KenLM context
 // (last order-1 word ids), and a rolling hash + length of the partial word.  When ' ' is a candidate symbol the
 // partial word of every beam is looked up in the vocabulary table and scored once per frame (commit_*); candidates
-// are ranked by acoustic + lm(text) + partial-word penalty, beams keep the acoustic score.  pyctcdecode caches
-// lm(text) by text, so a text first seen at the end of the utterance is the only one that gets the </s> term: the
-// per-utterance `seen` hash set (global memory) records every text committed during the search.
+// are ranked by acoustic + lm(text) + partial-word penalty, beams keep the acoustic score.  At the end of the utterance
+// every final text is scored once more as the end of the sentence (pyctcdecode >= 0.5 keys its LM cache by
+// (text, is_eos)): a pending partial word is committed with the </s> term, a text without one gets the </s> term alone.
 //
 // A beam is a CTC state (prefix, last_char).  Prefixes are identified by a 64-bit rolling hash of their symbol
 // sequence (merging = equal hash + equal last_char); the text is recovered at the end by back-tracing per-frame
@@ -150,13 +150,16 @@ __device__ __forceinline__ int vocab_lookup(const DeviceLM& lm, unsigned long lo
 }
 struct LmParams {
     double alpha, beta, unk, log10_to_ln;
-    unsigned long long* seen;            // [B][seen_cap] hash set of committed texts
-    int seen_cap;                        // power of two
 };
 // lm(text + word) from lm(text): (prev + alpha * raw * ln10) + beta, raw in log10 units (pyctcdecode LanguageModel.score)
 __device__ __forceinline__ double lm_accumulate(const LmParams& q, double prev, double raw)
 {
     return __dadd_rn(__dadd_rn(prev, __dmul_rn(__dmul_rn(q.alpha, raw), q.log10_to_ln)), q.beta);
+}
+// </s> on a text that has no pending word: alpha * ln P(</s> | context), no word-insertion bonus (no word is added)
+__device__ __forceinline__ double lm_accumulate_eos(const LmParams& q, double prev, double raw_eos)
+{
+    return __dadd_rn(prev, __dmul_rn(__dmul_rn(q.alpha, raw_eos), q.log10_to_ln));
 }
 __device__ __forceinline__ double partial_penalty(const LmParams& q, int wl)      // score_partial_token, char trie absent
 {
@@ -205,7 +208,6 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
     const float* lpb = logp + (size_t)b * T * V1;
     unsigned char* bpp = bp_parent + (size_t)b * T * BW_MAX;
     unsigned char* bps = bp_sym + (size_t)b * T * BW_MAX;
-    unsigned long long* seen = LM ? q.seen + (size_t)b * q.seen_cap : nullptr;
     const float clip_lo = logf(1e-15f);
     const int nkeep = LM ? lm.order - 1 : 0;               // KenLM context length
     // frames of THIS utterance: a zero-padded batch must decode every utterance over the frames the reference sees
@@ -292,14 +294,6 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
         // ---- 1b. LM: score the word every beam would commit on ' ' (once per beam and frame) ------------------
         if (LM && s.has_space && tid < n && s.wplen[tid] > 0) {
             commit_word(tid, false);
-            // pyctcdecode caches lm(text) for every candidate, kept or not: remember the committed text
-            const unsigned long long h = mix(s.hash[tid], space_id);
-            unsigned int slot = (unsigned int)(h & (unsigned long long)(q.seen_cap - 1));
-            while (true) {
-                const unsigned long long old = atomicCAS(seen + slot, 0ull, h);
-                if (old == 0ull || old == h) break;
-                slot = (slot + 1) & (unsigned int)(q.seen_cap - 1);
-            }
         }
 
         // ---- 2. expansion, insertion index = cand * n + beam (symbol-major like the reference loop) ------------
@@ -437,19 +431,12 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
     }
 
     // ---- end of utterance: the partial word joins the text; states with equal text merge (first-seen order);
-    //      with an LM the text is scored (a text never committed during the search gets the </s> term), the
-    //      best text wins; back-trace -----------------------------------------------------------------------------
-    if (LM && tid < s.nbeam && s.wplen[tid] > 0) {
-        const unsigned long long h = mix(s.hash[tid], space_id);
-        unsigned int slot = (unsigned int)(h & (unsigned long long)(q.seen_cap - 1));
-        bool was_seen = false;
-        while (true) {
-            const unsigned long long k = seen[slot];
-            if (k == h) { was_seen = true; break; }
-            if (k == 0ull) break;
-            slot = (slot + 1) & (unsigned int)(q.seen_cap - 1);
-        }
-        commit_word(tid, !was_seen);
+    //      with an LM every final text is scored with the </s> term, the best text wins; back-trace ---------------
+    if (LM && tid < s.nbeam) {
+        // every final text is scored as the END of the sentence: pyctcdecode >= 0.5 keys its LM cache by
+        // (text, is_eos), so a text that was already committed during the search is scored again with </s> at the end
+        if (s.wplen[tid] > 0) commit_word(tid, true);
+        else s.commit_lm[tid] = lm_accumulate_eos(q, s.lmscore[tid], lm_score(lm, s.ctx[tid], s.nctx[tid], lm.eos));
     }
     __syncthreads();
     if (tid == 0) {
@@ -461,7 +448,7 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
             if (!first) continue;
             double acc = s.score[i];
             for (int qq = i + 1; qq < n; ++qq) if (s.fhash[qq] == s.fhash[i]) acc = logaddexp_d(acc, s.score[qq]);
-            if (LM) acc = __dadd_rn(acc, s.wplen[i] > 0 ? s.commit_lm[i] : s.lmscore[i]);
+            if (LM) acc = __dadd_rn(acc, s.commit_lm[i]);
             if (acc > bs) { bs = acc; bi = i; }
         }
         int* oid = out_ids + (size_t)b * T;
@@ -585,13 +572,6 @@ extern "C" int vasr_lm_score_batch(const vasr_lm* h, const int32_t* ctx, const i
     return VASR_OK;
 }
 
-static size_t seen_capacity(int T, int beam_width)
-{
-    size_t need = (size_t)2 * T * beam_width, cap = 1024;
-    while (cap < need) cap <<= 1;
-    return cap;
-}
-
 extern "C" size_t vasr_ctc_beam_workspace_bytes(int B, int T)
 {
     if (B <= 0 || T <= 0) return 0;
@@ -601,8 +581,7 @@ extern "C" size_t vasr_ctc_beam_workspace_bytes(int B, int T)
 extern "C" size_t vasr_ctc_beam_lm_workspace_bytes(int B, int T, int beam_width)
 {
     if (B <= 0 || T <= 0 || beam_width <= 0) return 0;
-    const size_t bp = ((size_t)2 * B * T * vasr::beam::BW_MAX + 255) / 256 * 256;
-    return bp + (size_t)B * seen_capacity(T, beam_width) * sizeof(unsigned long long);
+    return ((size_t)2 * B * T * vasr::beam::BW_MAX + 255) / 256 * 256;     // same back-pointer records as without LM
 }
 
 static int beam_launch(const float* log_probs, const int32_t* frames, int B, int T, int V1, int blank, int space_id, int beam_width,
@@ -633,11 +612,7 @@ static int beam_launch(const float* log_probs, const int32_t* frames, int B, int
     unsigned char* bp_sym = bp_parent + (size_t)B * T * BW_MAX;
     LmParams q{};
     if (lm) {
-        const size_t bp = ((size_t)2 * B * T * BW_MAX + 255) / 256 * 256;
         q.alpha = alpha; q.beta = beta; q.unk = unk_score_offset; q.log10_to_ln = 1.0 / log10(M_E);
-        q.seen = (unsigned long long*)((unsigned char*)workspace + bp);
-        q.seen_cap = (int)seen_capacity(T, beam_width);
-        VASR_CUDA_OK(cudaMemsetAsync(q.seen, 0, (size_t)B * q.seen_cap * sizeof(unsigned long long), st));
         beam_kernel<true><<<B, THREADS, smem, st>>>(log_probs, frames, T, V1, blank, space_id, beam_width, token_min_logp,
                                                     beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score, lm->dev, q);
     } else {

@@ -25,6 +25,7 @@ struct vasr_frontend {
     int* d_mel_cnt = nullptr;      // [nfilt]
     float* d_mel_w = nullptr;      // [nfilt][max_nz]
     size_t stft_smem = 0;
+    int pad_per_utterance = 0;     // vasr_frontend_set_padding: reflect every row at its own length instead of at L
 };
 
 namespace vasr {
@@ -32,7 +33,7 @@ namespace vasr {
 // K1: grid (ceil(T_frames / 16), B), block 256.
 // smem: z[FE_PAIRS][512] float2 | tw[256] float2 | seg[(FE_FRAMES-1)*hop + win]
 __global__ void __launch_bounds__(FE_THREADS)
-stft_mel_kernel(const float* __restrict__ wave, long long L, int T_frames, int T_out,
+stft_mel_kernel(const float* __restrict__ wave, const long long* __restrict__ length, long long L, int T_frames, int T_out,
                 const float* __restrict__ window, const float2* __restrict__ twiddle,
                 const int* __restrict__ mel_start, const int* __restrict__ mel_cnt,
                 const float* __restrict__ mel_w, int max_nz, int nfilt, int win, int hop,
@@ -48,6 +49,9 @@ stft_mel_kernel(const float* __restrict__ wave, long long L, int T_frames, int T
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * FE_FRAMES;
     const float* x = wave + (long long)b * L;
+    // end of the signal for the reflection: the padded row (torch.stft on the [B, L] tensor, features.py:181-188), or -
+    // per-utterance mode - this utterance's own length, i.e. what it sees when the reference transcribes it alone
+    const long long Lr = length ? max(min(length[b], L), 1ll) : L;
 
     // ---- stage 0: pre-emphasised, reflect-padded signal segment ------------------
     // frame t uses y[hop*t - win/2 + m], m in [0, win)   (torch.stft centre padding n_fft/2,
@@ -56,9 +60,9 @@ stft_mel_kernel(const float* __restrict__ wave, long long L, int T_frames, int T
     for (int s = tid; s < seg_len; s += FE_THREADS) {
         long long i = i_base + s;
         if (i < 0) i = -i;
-        if (i >= L) i = 2 * (L - 1) - i;
+        if (i >= Lr) i = 2 * (Lr - 1) - i;
         float v = 0.f;
-        if (i >= 0 && i < L) {
+        if (i >= 0 && i < Lr) {
             v = x[i];
             if (i > 0) v = v - preemph * x[i - 1];   // features.py:255
         }
@@ -307,6 +311,13 @@ extern "C" void vasr_frontend_destroy(vasr_frontend* fe)
     delete fe;
 }
 
+extern "C" int vasr_frontend_set_padding(vasr_frontend* fe, int per_utterance)
+{
+    if (!fe) return vasr::set_error(VASR_EINVAL, "vasr_frontend_set_padding: null handle");
+    fe->pad_per_utterance = per_utterance ? 1 : 0;
+    return VASR_OK;
+}
+
 extern "C" int vasr_frontend_num_frames(const vasr_frontend* fe, int64_t L)
 {
     if (!fe || L < 0) return vasr::set_error(VASR_EINVAL, "vasr_frontend_num_frames: bad argument");
@@ -330,7 +341,7 @@ extern "C" int vasr_frontend_forward(vasr_frontend* fe, const float* wave, const
     const int T_out = vasr_frontend_num_frames(fe, L);
     dim3 grid(ceil_div(T_frames, FE_FRAMES), B);
     stft_mel_kernel<<<grid, FE_THREADS, fe->stft_smem, st>>>(
-        wave, (long long)L, T_frames, T_out, fe->d_window, fe->d_twiddle, fe->d_mel_start, fe->d_mel_cnt,
+        wave, fe->pad_per_utterance ? (const long long*)length : nullptr, (long long)L, T_frames, T_out, fe->d_window, fe->d_twiddle, fe->d_mel_start, fe->d_mel_cnt,
         fe->d_mel_w, fe->max_nz, fe->cfg.nfilt, fe->cfg.n_window_size, hop, fe->cfg.preemph,
         fe->cfg.log_zero_guard, feat);
     VASR_LAUNCH_OK("stft_mel_kernel");

@@ -96,7 +96,12 @@ class VietASR:
     def __init__(self, config_file: Optional[str] = None, encoder_checkpoint: Optional[str] = None,
                  decoder_checkpoint: Optional[str] = None, device: str = "gpu", lm_path: Optional[str] = None,
                  beam_width: int = 20, lm_alpha: float = 0.5, lm_beta: float = 1.5, *,
-                 model_definition: Optional[Dict] = None, gemm_mode: str = "f16x3", decoder: str = "beam"):
+                 model_definition: Optional[Dict] = None, gemm_mode: str = "f16x3", decoder: str = "beam",
+                 batch_invariant: bool = False):
+        """`batch_invariant=True`: zero-padded batches are processed so that every utterance gets exactly the result it
+        gets alone (the only way the reference ever runs, infer.py:167-171): the STFT reflects at each utterance's own
+        length (`set_padding`) in addition to the per-utterance decoding frames that are always on.  Default False =
+        the reference's tensor semantics for a [B, L] batch (features.py:181-188)."""
         if device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("vasr_b200.VietASR runs on a CUDA device only (device='gpu'); there is no CPU path")
         if lm_path is not None and not os.path.exists(lm_path):
@@ -116,6 +121,9 @@ class VietASR:
         self.labels: List[str] = list(md["labels"])
         self.sample_rate = pre["sample_rate"]
         self.preprocessor = asr.AudioToMelSpectrogramPreprocessor(**pre)
+        self.batch_invariant = bool(batch_invariant)
+        if self.batch_invariant:
+            self.preprocessor.set_padding(True)
         self.encoder = asr.JasperEncoder(feat_in=pre["features"], gemm_mode=gemm_mode, **md["JasperEncoder"])
         self.decoder = asr.JasperDecoderForCTC(feat_in=md["JasperEncoder"]["jasper"][-1]["filters"],
                                                num_classes=len(self.labels))
