@@ -419,6 +419,29 @@ def test_beam_search_edge_cases():
     assert got[1] == "" and got[2] == "" and got[4] == "hi there"
 
 
+def test_beam_search_widest_expansion_matches_oracle():
+    """128 beams x 16 candidate symbols per frame (the kernel's expansion limit, 2048 candidate states per frame): the
+    merge table at its highest load and the ranking over ~2000 merged states, on flat and on diffuse posteriors."""
+    V = _cuda()
+    from oracle import beam_oracle as BO
+    labels = V.configs.EN_LABELS
+    g = torch.Generator().manual_seed(11)
+    T, V1 = 24, len(labels) + 1
+    flat = torch.zeros(T, V1).log_softmax(-1)
+    diffuse = (0.5 * torch.randn(T, V1, generator=g)).log_softmax(-1)          # ~all symbols above token_min_logp
+    mixed = (2.0 * torch.randn(T, V1, generator=g)).log_softmax(-1)
+    lp = torch.stack([flat, diffuse, mixed])
+    ids, n, score = V.ctc_beam_search(lp.cuda(), labels, 128)
+    got = [" ".join(t.split()) for t in V.ids_to_text(ids, n, labels)]
+    for b in range(lp.shape[0]):
+        want, want_score = BO.beam_search_no_lm(lp[b].numpy(), labels, 128)
+        assert got[b] == want, b
+        assert abs(score[b].item() - want_score) < 1e-3 * max(1.0, abs(want_score))
+    # deterministic: shared-memory atomics decide nothing that reaches the result
+    ids2, n2, score2 = V.ctc_beam_search(lp.cuda(), labels, 128)
+    assert torch.equal(ids, ids2) and torch.equal(n, n2) and torch.equal(score, score2)
+
+
 def test_beam_module_and_engine():
     V = _cuda()
     from oracle import beam_oracle as BO

@@ -17,8 +17,10 @@
 // A beam is a CTC state (prefix, last_char).  Prefixes are identified by a 64-bit rolling hash of their symbol
 // sequence (merging = equal hash + equal last_char); the text is recovered at the end by back-tracing per-frame
 // (parent beam, appended symbol) records.  Per frame: candidate symbols {logp >= token_min_logp} U {argmax} in
-// ascending index, expansion in (symbol, beam) order, merge by log-sum-exp in first-seen order (bitonic sort on
-// (key, insertion index)), prune at best + beam_prune_logp, keep the beam_width best (ties keep first-seen order).
+// ascending index, expansion in (symbol, beam) order, merge by log-sum-exp in first-seen order (hash table in shared
+// memory, members reduced in insertion order), prune at best + beam_prune_logp, keep the beam_width best (ties keep
+// first-seen order; rank by counting).  Round 1 did the merge and the ranking with two bitonic sorts per frame
+// (~100 block barriers, 49 us per frame); this version has 6 barriers per frame.
 #include "common.cuh"
 #include "kernels.cuh"
 #include <math.h>
@@ -53,25 +55,6 @@ __device__ __forceinline__ unsigned long long dkey(double x)
 {
     unsigned long long u = (unsigned long long)__double_as_longlong(x);
     return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
-}
-
-// ascending bitonic sort of (k1, k2) pairs, n a power of two
-__device__ void bitonic_sort(unsigned long long* k1, unsigned int* k2, int n)
-{
-    for (int k = 2; k <= n; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += THREADS) {
-                const int x = i ^ j;
-                if (x > i) {
-                    const bool up = (i & k) == 0;
-                    const unsigned long long a1 = k1[i], b1 = k1[x];
-                    const unsigned int a2 = k2[i], b2 = k2[x];
-                    const bool gt = (a1 > b1) || (a1 == b1 && a2 > b2);
-                    if (gt == up) { k1[i] = b1; k1[x] = a1; k2[i] = b2; k2[x] = a2; }
-                }
-            }
-            __syncthreads();
-        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -167,34 +150,68 @@ __device__ __forceinline__ double partial_penalty(const LmParams& q, int wl)    
     return wl > 6 ? __ddiv_rn(__dmul_rn(q.unk, (double)wl), 6.0) : q.unk;
 }
 
-struct Smem {
+// the state of the (at most beam_width) beams between two frames; two sets alternate (frame t reads set t & 1 and
+// writes the other), so a frame needs no copy-back pass
+struct BeamSet {
     unsigned long long hash[BW_MAX], fhash[BW_MAX];       // fhash: hash of the text without a trailing space
     double score[BW_MAX];
     unsigned char lastsym[BW_MAX], lastkey[BW_MAX];
-    unsigned long long nhash[BW_MAX], nfhash[BW_MAX];
-    double nscore[BW_MAX];
-    unsigned char nlastsym[BW_MAX], nlastkey[BW_MAX];
     // LM state per beam (unused without LM)
-    double lmscore[BW_MAX], nlmscore[BW_MAX], commit_lm[BW_MAX];
-    unsigned long long wph[BW_MAX], nwph[BW_MAX];
-    int wplen[BW_MAX], nwplen[BW_MAX];
-    int ctx[BW_MAX][MAX_ORDER - 1], nctx_[BW_MAX][MAX_ORDER - 1], commit_ctx[BW_MAX][MAX_ORDER - 1];
-    int nctx[BW_MAX], nnctx[BW_MAX], commit_nctx[BW_MAX];
+    double lmscore[BW_MAX];
+    unsigned long long wph[BW_MAX];
+    int wplen[BW_MAX];
+    int ctx[BW_MAX][MAX_ORDER - 1];
+    int nctx[BW_MAX];
+};
+constexpr unsigned EMPTY = 0xFFFFu;      // > every insertion index (< NC_MAX = 2048)
+constexpr int TABLE_MAX = 2 * NC_MAX;    // merge table: open addressing at a load factor <= 1/2
+struct Smem {
+    BeamSet bs[2];
+    double commit_lm[BW_MAX];
+    int commit_ctx[BW_MAX][MAX_ORDER - 1];
+    int commit_nctx[BW_MAX];
     int has_space;
-    double ucomb[NC_MAX];                // ranking score by unique slot
     float lp[128];
     int cand[MC];
     float candp[MC];
-    int ncand, nbeam, nuniq, nkept;
-    unsigned long long ckey[NC_MAX];     // merge key, later the ranking key
-    unsigned int cidx[NC_MAX];           // insertion index
-    double cscore[NC_MAX];               // by insertion index
-    unsigned int cmeta[NC_MAX];          // by insertion index: src beam | appended sym << 8 | lastsym << 16 | lastkey << 24
-    double uscore[NC_MAX];               // merged score by unique slot
-    unsigned int urep[NC_MAX];           // representative insertion index by unique slot
-    int scan[THREADS / 32];
+    int ncand, nbeam, nalive, nsurv;
+    int sel_digit, sel_need, sel_cnt;    // radix select: digit of the bucket holding the beam_width-th key, what is still needed from it, its size
+    unsigned int hist[256];
+    double wbest[THREADS / 32];
+    // by insertion index (candidate = symbol-major (cand, beam) pair)
+    union {
+        unsigned long long ckey[NC_MAX]; // merge key of the candidate's state (phases 2-3)
+        double ucomb[NC_MAX];            // ranking score of a merged state, at its first-seen candidate (phases 4-5)
+        unsigned long long surv_key[NC_MAX];    // phase 6, many states alive: the ones the radix select kept
+    };
+    double cscore[NC_MAX];               // acoustic score; after the merge the first-seen candidate holds the merged score
+    unsigned int cmeta[NC_MAX];          // src beam | appended sym << 8 | lastsym << 16 | lastkey << 24
+    union {
+        unsigned short cslot[NC_MAX];    // table slot of the candidate's state (phases 3-4)
+        unsigned short surv_idx[NC_MAX]; // phase 6: first-seen candidate of the states the radix select kept
+    };
+    unsigned short next[NC_MAX];         // next candidate in the slot's member list (EMPTY = end)
+    union {
+        unsigned int table[TABLE_MAX];   // slot -> a member of the state stored there, in the end its FIRST-SEEN member
+        unsigned long long alive_key[NC_MAX];   // after the merge: order-preserving keys of the states that survive pruning
+    };
+    union {
+        unsigned int head[TABLE_MAX];    // slot -> most recently pushed member
+        unsigned short alive_idx[NC_MAX];       // after the merge: first-seen candidate of every surviving state
+    };
 };
 
+// One CTA per utterance, T_e sequential frames.  A frame is six block-wide phases (no sort):
+//   1. warp 0 clips the frame's log-probs and picks the candidate symbols; the other warps clear the merge table
+//   2. expansion of (symbol, beam) pairs into candidate states (+ LM: the word every beam would commit on ' ')
+//   3. merge: every candidate inserts its 64-bit state key into an open-addressing table in shared memory; the slot
+//      keeps the lowest insertion index (atomicMin) and a linked list of its members
+//   4. the first-seen member of every state log-sum-exps the members IN INSERTION ORDER (what a sort by
+//      (key, insertion index) followed by a run-wise reduction gives - the order matters for bit-equal float64 sums)
+//   5. states within beam_prune_logp of the best are collected; each finds its rank by counting the states that
+//      precede it in (score descending, first-seen ascending) order - O(A^2 / 256) compares on shared-memory
+//      broadcasts, A ~ 100-400 - which is the position a stable sort would give it
+//   6. ranks < beam_width become the beams of the next frame (other beam set) and write their back-pointers
 template <bool LM>
 __global__ void __launch_bounds__(THREADS)
 beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int T, int V1, int blank, int space_id, int beam_width,
@@ -215,37 +232,40 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
     const int Tb = frames ? min(max(frames[b], 0), T) : T;
 
     if (tid == 0) {
-        s.hash[0] = H0; s.fhash[0] = H0; s.score[0] = 0.0; s.lastsym[0] = SYM_NONE; s.lastkey[0] = KEY_NONE; s.nbeam = 1;
+        BeamSet& z = s.bs[0];
+        z.hash[0] = H0; z.fhash[0] = H0; z.score[0] = 0.0; z.lastsym[0] = SYM_NONE; z.lastkey[0] = KEY_NONE; s.nbeam = 1;
         if (LM) {                                           // start state: <s> (score_boundary=True)
-            s.lmscore[0] = 0.0; s.wph[0] = H0; s.wplen[0] = 0;
-            s.nctx[0] = nkeep > 0 ? 1 : 0; s.ctx[0][0] = lm.bos;
+            z.lmscore[0] = 0.0; z.wph[0] = H0; z.wplen[0] = 0;
+            z.nctx[0] = nkeep > 0 ? 1 : 0; z.ctx[0][0] = lm.bos;
         }
     }
     __syncthreads();
 
     // the word a beam would commit if ' ' came next: id lookup, LM score, new context (one thread per beam)
-    auto commit_word = [&](int i, bool eos) {
-        const int wid_lm = vocab_lookup(lm, s.wph[i]);
+    auto commit_word = [&](const BeamSet& c, int i, bool eos) {
+        const int wid_lm = vocab_lookup(lm, c.wph[i]);
         const int w = wid_lm < 0 ? 0 : wid_lm;             // <unk> = 0
-        double r = lm_score(lm, s.ctx[i], s.nctx[i], w);
+        double r = lm_score(lm, c.ctx[i], c.nctx[i], w);
         if (wid_lm < 0) r = __dadd_rn(r, q.unk);            // `word not in kenlm_model`
         int nc = 0;
         if (nkeep > 0) {
-            const int have = s.nctx[i];
+            const int have = c.nctx[i];
             const int drop = have + 1 > nkeep ? have + 1 - nkeep : 0;
-            for (int j = drop; j < have; ++j) s.commit_ctx[i][nc++] = s.ctx[i][j];
+            for (int j = drop; j < have; ++j) s.commit_ctx[i][nc++] = c.ctx[i][j];
             s.commit_ctx[i][nc++] = w;
         }
         s.commit_nctx[i] = nc;
         if (eos) r = __dadd_rn(r, lm_score(lm, s.commit_ctx[i], nc, lm.eos));
-        s.commit_lm[i] = lm_accumulate(q, s.lmscore[i], r);
+        s.commit_lm[i] = lm_accumulate(q, c.lmscore[i], r);
     };
 
     for (int t = 0; t < Tb; ++t) {
-        // ---- 1. frame log-probs (clipped like log(clip(p, 1e-15, 1))) and candidate symbols -------------------
-        if (tid < V1) s.lp[tid] = fminf(fmaxf(lpb[(size_t)t * V1 + tid], clip_lo), 0.f);
-        __syncthreads();
+        const BeamSet& cur = s.bs[t & 1];
+        BeamSet& nxt = s.bs[(t & 1) ^ 1];
+        // ---- 1. frame log-probs (clipped like log(clip(p, 1e-15, 1))) and candidate symbols: warp 0 ------------
         if (wid == 0) {
+            for (int v = lane; v < V1; v += 32) s.lp[v] = fminf(fmaxf(lpb[(size_t)t * V1 + v], clip_lo), 0.f);
+            __syncwarp();
             // argmax, ties -> lowest index (np.argmax)
             float best = -INFINITY; int bi = 0x7fffffff;
             for (int v = lane; v < V1; v += 32) { const float x = s.lp[v]; if (x > best) { best = x; bi = v; } }
@@ -285,158 +305,222 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
                 sp = sp || (__ballot_sync(0xffffffffu, f && v == space_id) != 0u);
                 base += __popc(m);
             }
-            if (lane == 0) { s.ncand = base; s.has_space = sp ? 1 : 0; }
+            if (lane == 0) { s.ncand = base; s.has_space = sp ? 1 : 0; s.nalive = 0; s.nsurv = 0; }
+        } else {
+            // the other warps clear the part of the merge table this frame can touch (2 x the next power of two of
+            // nbeam * MC bounds 2 x Np below)
+            int cap = 1; while (cap < s.nbeam * MC) cap <<= 1;
+            cap *= 2;
+            const uint4 e4 = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+            uint4* t4 = reinterpret_cast<uint4*>(s.table);
+            uint4* h4 = reinterpret_cast<uint4*>(s.head);
+            for (int i = tid - 32; i < cap / 4; i += THREADS - 32) { t4[i] = e4; h4[i] = e4; }
         }
         __syncthreads();
         const int n = s.nbeam, m = s.ncand, N = n * m;
         int Np = 1; while (Np < N) Np <<= 1;
+        const unsigned mask = (unsigned)(2 * Np - 1);
 
-        // ---- 1b. LM: score the word every beam would commit on ' ' (once per beam and frame) ------------------
-        if (LM && s.has_space && tid < n && s.wplen[tid] > 0) {
-            commit_word(tid, false);
-        }
+        // ---- 2. LM: score the word every beam would commit on ' ' (once per beam and frame) --------------------
+        if (LM && s.has_space && tid < n && cur.wplen[tid] > 0) commit_word(cur, tid, false);
 
         // ---- 2. expansion, insertion index = cand * n + beam (symbol-major like the reference loop) ------------
-        for (int idx = tid; idx < Np; idx += THREADS) {
-            if (idx < N) {
-                const int j = idx / n, i = idx - j * n;
-                const int c = s.cand[j];
-                const unsigned long long h = s.hash[i];
-                const int ls = s.lastsym[i], lk = s.lastkey[i];
-                unsigned long long nh = h; int nls = ls, nlk, app = SYM_NONE;
-                if (c == blank) nlk = KEY_BLANK;
-                else if (lk == c) nlk = c;                                     // repeat of the last emitted symbol
-                else if (c == space_id) {
-                    if (h == H0 || ls == space_id) { nls = space_id; nlk = space_id; }   // leading / repeated space: no new word
-                    else { nh = mix(h, c); nls = c; nlk = c; app = c; }
-                } else { nh = mix(h, c); nls = c; nlk = c; app = c; }
-                s.ckey[idx] = mix(nh, nlk);
-                s.cidx[idx] = (unsigned)idx;
-                s.cscore[idx] = s.score[i] + (double)s.candp[j];
-                s.cmeta[idx] = (unsigned)i | ((unsigned)app << 8) | ((unsigned)nls << 16) | ((unsigned)nlk << 24);
-            } else { s.ckey[idx] = ~0ull; s.cidx[idx] = 0xffffffffu; }
+        for (int idx = tid; idx < N; idx += THREADS) {
+            const int j = idx / n, i = idx - j * n;
+            const int c = s.cand[j];
+            const unsigned long long h = cur.hash[i];
+            const int ls = cur.lastsym[i], lk = cur.lastkey[i];
+            unsigned long long nh = h; int nls = ls, nlk, app = SYM_NONE;
+            if (c == blank) nlk = KEY_BLANK;
+            else if (lk == c) nlk = c;                                     // repeat of the last emitted symbol
+            else if (c == space_id) {
+                if (h == H0 || ls == space_id) { nls = space_id; nlk = space_id; }   // leading / repeated space: no new word
+                else { nh = mix(h, c); nls = c; nlk = c; app = c; }
+            } else { nh = mix(h, c); nls = c; nlk = c; app = c; }
+            s.ckey[idx] = mix(nh, nlk);
+            s.cscore[idx] = cur.score[i] + (double)s.candp[j];
+            s.cmeta[idx] = (unsigned)i | ((unsigned)app << 8) | ((unsigned)nls << 16) | ((unsigned)nlk << 24);
         }
         __syncthreads();
 
-        // ---- 3. merge equal states: sort by (key, insertion index), log-sum-exp each run in first-seen order ---
-        bitonic_sort(s.ckey, s.cidx, Np);
-        // heads -> unique slots (ordered compaction via block scan)
-        int carry = 0;
-        for (int base = 0; base < Np; base += THREADS) {
-            const int p = base + tid;
-            const bool head = p < N && (p == 0 || s.ckey[p] != s.ckey[p - 1]);
-            const unsigned bal = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) s.scan[wid] = __popc(bal);
-            __syncthreads();
-            int off = carry;
-            for (int w = 0; w < wid; ++w) off += s.scan[w];
-            if (head) {
-                const int u = off + __popc(bal & ((1u << lane) - 1u));
-                double acc = s.cscore[s.cidx[p]];
-                for (int qq = p + 1; qq < N && s.ckey[qq] == s.ckey[p]; ++qq) acc = logaddexp_d(acc, s.cscore[s.cidx[qq]]);
-                s.uscore[u] = acc;
-                s.urep[u] = s.cidx[p];
-                // ranking score: acoustic, plus lm(text) and the partial-word penalty of the state when an LM is fused
-                double comb = acc;
-                if (LM) {
-                    const unsigned meta = s.cmeta[s.cidx[p]];
-                    const int src = meta & 0xff, app = (meta >> 8) & 0xff;
-                    double lmv; int wl;
-                    if (app == space_id) { lmv = s.commit_lm[src]; wl = 0; }
-                    else { lmv = s.lmscore[src]; wl = s.wplen[src] + (app != SYM_NONE ? 1 : 0); }
-                    comb = __dadd_rn(acc, __dadd_rn(lmv, partial_penalty(q, wl)));
+        // ---- 3. merge equal states: insert into the table; the slot ends up holding the first-seen member -------
+        for (int idx = tid; idx < N; idx += THREADS) {
+            const unsigned long long key = s.ckey[idx];
+            unsigned p = (unsigned)(key >> 20) & mask;
+            while (true) {
+                unsigned e = *reinterpret_cast<volatile unsigned*>(&s.table[p]);
+                if (e == EMPTY) {
+                    e = atomicCAS(&s.table[p], EMPTY, (unsigned)idx);
+                    if (e == EMPTY) break;                                 // claimed an empty slot
                 }
-                s.ucomb[u] = comb;
+                if (s.ckey[e] == key) { atomicMin(&s.table[p], (unsigned)idx); break; }   // any member carries the key
+                p = (p + 1) & mask;
             }
-            int tot = 0;
-            for (int w = 0; w < THREADS / 32; ++w) tot += s.scan[w];
-            carry += tot;
-            __syncthreads();
+            s.cslot[idx] = (unsigned short)p;
+            s.next[idx] = (unsigned short)atomicExch(&s.head[p], (unsigned)idx);
         }
-        const int U = carry;
+        __syncthreads();
 
-        // ---- 4. prune at best + beam_prune_logp, rank by (score desc, first-seen order) ------------------------
+        // ---- 4. first-seen members: log-sum-exp of the members in insertion order, ranking score ----------------
+        unsigned own = 0;                                                  // bit k: candidate tid + k * THREADS is a first-seen member
         double best = -INFINITY;
-        for (int u = tid; u < U; u += THREADS) best = fmax(best, s.ucomb[u]);
+        for (int idx = tid, k = 0; idx < N; idx += THREADS, ++k) {
+            const unsigned p = s.cslot[idx];
+            if (s.table[p] != (unsigned)idx) continue;
+            own |= 1u << k;
+            double acc = s.cscore[idx];
+            int last = idx;
+            while (true) {                                                 // next member in ascending insertion index
+                int pick = 0x7fffffff;
+                for (unsigned e = s.head[p]; e != EMPTY; e = s.next[e])
+                    if ((int)e > last && (int)e < pick) pick = (int)e;
+                if (pick == 0x7fffffff) break;
+                acc = logaddexp_d(acc, s.cscore[pick]);
+                last = pick;
+            }
+            s.cscore[idx] = acc;
+            // ranking score: acoustic, plus lm(text) and the partial-word penalty of the state when an LM is fused
+            double comb = acc;
+            if (LM) {
+                const unsigned meta = s.cmeta[idx];
+                const int src = meta & 0xff, app = (meta >> 8) & 0xff;
+                double lmv; int wl;
+                if (app == space_id) { lmv = s.commit_lm[src]; wl = 0; }
+                else { lmv = cur.lmscore[src]; wl = cur.wplen[src] + (app != SYM_NONE ? 1 : 0); }
+                comb = __dadd_rn(acc, __dadd_rn(lmv, partial_penalty(q, wl)));
+            }
+            s.ucomb[idx] = comb;
+            best = fmax(best, comb);
+        }
         for (int o = 16; o >= 1; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-        __shared__ double wbest[THREADS / 32];
-        if (lane == 0) wbest[wid] = best;
+        if (lane == 0) s.wbest[wid] = best;
         __syncthreads();
-        best = wbest[0];
-        for (int w = 1; w < THREADS / 32; ++w) best = fmax(best, wbest[w]);
-        int Up = 1; while (Up < U) Up <<= 1;
-        for (int u = tid; u < Up; u += THREADS) {
-            if (u < U && s.ucomb[u] >= best + (double)prune) {
-                s.ckey[u] = ~dkey(s.ucomb[u]);             // ascending sort == descending score
-                s.cidx[u] = s.urep[u];
-            } else { s.ckey[u] = ~0ull; s.cidx[u] = 0xffffffffu; }
+        best = s.wbest[0];
+        for (int w = 1; w < THREADS / 32; ++w) best = fmax(best, s.wbest[w]);
+
+        // ---- 5. prune at best + beam_prune_logp -----------------------------------------------------------------
+        const double thr = best + (double)prune;
+        for (int idx = tid, k = 0; idx < N; idx += THREADS, ++k) {
+            if (!((own >> k) & 1u)) continue;
+            const double c = s.ucomb[idx];
+            if (c >= thr) {
+                const int a = atomicAdd(&s.nalive, 1);
+                s.alive_key[a] = dkey(c);
+                s.alive_idx[a] = (unsigned short)idx;
+            }
         }
         __syncthreads();
-        bitonic_sort(s.ckey, s.cidx, Up);
 
-        // ---- 5. new beams + back-pointers --------------------------------------------------------------------
-        // cidx now holds representative insertion indices in rank order; the merged (acoustic) score of a
-        // representative is stored at the representative's insertion slot
-        for (int u = tid; u < U; u += THREADS) s.cscore[s.urep[u]] = s.uscore[u];
-        __syncthreads();
-        int kept = 0;
-        for (int k = tid; k < BW_MAX; k += THREADS) {
-            const bool ok = k < Up && k < beam_width && s.cidx[k] != 0xffffffffu;
-            if (ok) {
-                const unsigned rep = s.cidx[k];
-                const unsigned meta = s.cmeta[rep];
-                const int src = meta & 0xff, app = (meta >> 8) & 0xff;
-                const unsigned long long nh = (app == SYM_NONE) ? s.hash[src] : mix(s.hash[src], app);
-                s.nhash[k] = nh;
-                // text without a trailing space: unchanged by a committed ' ' (the source cannot end in one)
-                s.nfhash[k] = (app == SYM_NONE) ? s.fhash[src] : (app == space_id ? s.hash[src] : nh);
-                s.nscore[k] = s.cscore[rep];
-                s.nlastsym[k] = (unsigned char)((meta >> 16) & 0xff);
-                s.nlastkey[k] = (unsigned char)((meta >> 24) & 0xff);
-                if (LM) {
-                    if (app == space_id) {
-                        s.nlmscore[k] = s.commit_lm[src]; s.nwph[k] = H0; s.nwplen[k] = 0;
-                        s.nnctx[k] = s.commit_nctx[src];
-                        for (int j = 0; j < MAX_ORDER - 1; ++j) s.nctx_[k][j] = s.commit_ctx[src][j];
-                    } else {
-                        s.nlmscore[k] = s.lmscore[src];
-                        s.nwph[k] = (app == SYM_NONE) ? s.wph[src] : mix(s.wph[src], app);
-                        s.nwplen[k] = s.wplen[src] + (app != SYM_NONE ? 1 : 0);
-                        s.nnctx[k] = s.nctx[src];
-                        for (int j = 0; j < MAX_ORDER - 1; ++j) s.nctx_[k][j] = s.ctx[src][j];
+        // ---- 6. rank by (score descending, first-seen ascending); the beam_width best become the new beams ------
+        const int A = s.nalive;
+        const unsigned long long* rkey = s.alive_key;
+        const unsigned short* ridx = s.alive_idx;
+        int R = A;
+        if (A > 2 * BW_MAX) {
+            // many states alive (diffuse posteriors): counting ranks among all of them is O(A^2).  Radix-select the
+            // key of the beam_width-th best state first, 8 bits at a time from the highest bit in which the alive
+            // keys can differ (they all lie between the keys of thr and best), and rank only the states at or above
+            // it.  The select stops as soon as the bucket that holds the beam_width-th key plus everything above it
+            // is at most 2 x BW_MAX states; states with equal scores stay together, the counting below orders them.
+            const unsigned long long kbest = dkey(best), kthr = dkey(thr);
+            const int hb = 63 - __clzll((long long)(kbest ^ kthr));         // -1: all alive keys are equal
+            int shift = hb < 0 ? -8 : (hb / 8) * 8;
+            unsigned long long pmask = shift >= 56 ? 0ull : (~0ull << (shift + 8));
+            unsigned long long prefix = kbest & pmask;
+            static_assert(THREADS == 256, "one histogram bin per thread");
+            if (tid == 0) s.sel_need = beam_width;
+            for (; shift >= 0; shift -= 8) {
+                s.hist[tid] = 0u;
+                __syncthreads();
+                for (int a = tid; a < A; a += THREADS) {
+                    const unsigned long long ka = s.alive_key[a];
+                    if ((ka & pmask) == prefix) atomicAdd(&s.hist[(unsigned)(ka >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (wid == 0) {
+                    unsigned c = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) c += s.hist[lane * 8 + j];
+                    unsigned above = c;                                      // inclusive suffix sum over the lanes
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_down_sync(0xffffffffu, above, o);
+                        if (lane + o < 32) above += v;
+                    }
+                    above -= c;                                              // states in higher buckets than this lane's
+                    const unsigned need = (unsigned)s.sel_need;
+                    __syncwarp();
+                    if (above < need && need <= above + c) {                 // exactly one lane
+                        unsigned acc = above;
+                        for (int j = 7; j >= 0; --j) {
+                            const unsigned hcnt = s.hist[lane * 8 + j];
+                            if (need <= acc + hcnt) { s.sel_digit = lane * 8 + j; s.sel_need = (int)(need - acc); s.sel_cnt = (int)hcnt; break; }
+                            acc += hcnt;
+                        }
                     }
                 }
-                bpp[(size_t)t * BW_MAX + k] = (unsigned char)src;
-                bps[(size_t)t * BW_MAX + k] = (unsigned char)app;
+                __syncthreads();
+                prefix |= (unsigned long long)s.sel_digit << shift;
+                pmask |= 0xFFull << shift;
+                if ((beam_width - s.sel_need) + s.sel_cnt <= 2 * BW_MAX) break;
             }
-            kept += ok ? 1 : 0;
+            for (int a = tid; a < A; a += THREADS) {
+                const unsigned long long ka = s.alive_key[a];
+                if ((ka & pmask) >= prefix) {
+                    const int u = atomicAdd(&s.nsurv, 1);
+                    s.surv_key[u] = ka;
+                    s.surv_idx[u] = s.alive_idx[a];
+                }
+            }
+            __syncthreads();
+            rkey = s.surv_key; ridx = s.surv_idx; R = s.nsurv;
         }
-        // count survivors
-        {
-            int c = kept;
-            for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) s.scan[wid] = c;
-        }
-        __syncthreads();
-        if (tid == 0) { int tot = 0; for (int w = 0; w < THREADS / 32; ++w) tot += s.scan[w]; s.nbeam = tot; }
-        for (int k = tid; k < BW_MAX; k += THREADS) {
-            s.hash[k] = s.nhash[k]; s.fhash[k] = s.nfhash[k]; s.score[k] = s.nscore[k];
-            s.lastsym[k] = s.nlastsym[k]; s.lastkey[k] = s.nlastkey[k];
+        for (int a = tid; a < R; a += THREADS) {
+            const unsigned long long ka = rkey[a];
+            const unsigned ia = ridx[a];
+            int k = 0;
+            for (int o = 0; o < R; ++o) {
+                const unsigned long long ko = rkey[o];
+                const unsigned io = ridx[o];
+                k += (ko > ka || (ko == ka && io < ia)) ? 1 : 0;
+            }
+            if (k >= beam_width) continue;
+            const unsigned meta = s.cmeta[ia];
+            const int src = meta & 0xff, app = (meta >> 8) & 0xff;
+            const unsigned long long nh = (app == SYM_NONE) ? cur.hash[src] : mix(cur.hash[src], app);
+            nxt.hash[k] = nh;
+            // text without a trailing space: unchanged by a committed ' ' (the source cannot end in one)
+            nxt.fhash[k] = (app == SYM_NONE) ? cur.fhash[src] : (app == space_id ? cur.hash[src] : nh);
+            nxt.score[k] = s.cscore[ia];
+            nxt.lastsym[k] = (unsigned char)((meta >> 16) & 0xff);
+            nxt.lastkey[k] = (unsigned char)((meta >> 24) & 0xff);
             if (LM) {
-                s.lmscore[k] = s.nlmscore[k]; s.wph[k] = s.nwph[k]; s.wplen[k] = s.nwplen[k]; s.nctx[k] = s.nnctx[k];
-                for (int j = 0; j < MAX_ORDER - 1; ++j) s.ctx[k][j] = s.nctx_[k][j];
+                if (app == space_id) {
+                    nxt.lmscore[k] = s.commit_lm[src]; nxt.wph[k] = H0; nxt.wplen[k] = 0;
+                    nxt.nctx[k] = s.commit_nctx[src];
+                    for (int j = 0; j < MAX_ORDER - 1; ++j) nxt.ctx[k][j] = s.commit_ctx[src][j];
+                } else {
+                    nxt.lmscore[k] = cur.lmscore[src];
+                    nxt.wph[k] = (app == SYM_NONE) ? cur.wph[src] : mix(cur.wph[src], app);
+                    nxt.wplen[k] = cur.wplen[src] + (app != SYM_NONE ? 1 : 0);
+                    nxt.nctx[k] = cur.nctx[src];
+                    for (int j = 0; j < MAX_ORDER - 1; ++j) nxt.ctx[k][j] = cur.ctx[src][j];
+                }
             }
+            bpp[(size_t)t * BW_MAX + k] = (unsigned char)src;
+            bps[(size_t)t * BW_MAX + k] = (unsigned char)app;
         }
+        if (tid == 0) s.nbeam = A < beam_width ? A : beam_width;
         __syncthreads();
     }
+    const BeamSet& fin = s.bs[Tb & 1];
 
     // ---- end of utterance: the partial word joins the text; states with equal text merge (first-seen order);
     //      with an LM every final text is scored with the </s> term, the best text wins; back-trace ---------------
     if (LM && tid < s.nbeam) {
         // every final text is scored as the END of the sentence: pyctcdecode >= 0.5 keys its LM cache by
         // (text, is_eos), so a text that was already committed during the search is scored again with </s> at the end
-        if (s.wplen[tid] > 0) commit_word(tid, true);
-        else s.commit_lm[tid] = lm_accumulate_eos(q, s.lmscore[tid], lm_score(lm, s.ctx[tid], s.nctx[tid], lm.eos));
+        if (fin.wplen[tid] > 0) commit_word(fin, tid, true);
+        else s.commit_lm[tid] = lm_accumulate_eos(q, fin.lmscore[tid], lm_score(lm, fin.ctx[tid], fin.nctx[tid], lm.eos));
     }
     __syncthreads();
     if (tid == 0) {
@@ -444,10 +528,10 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
         int bi = 0; double bs = -INFINITY;
         for (int i = 0; i < n; ++i) {
             bool first = true;
-            for (int qq = 0; qq < i; ++qq) if (s.fhash[qq] == s.fhash[i]) { first = false; break; }
+            for (int qq = 0; qq < i; ++qq) if (fin.fhash[qq] == fin.fhash[i]) { first = false; break; }
             if (!first) continue;
-            double acc = s.score[i];
-            for (int qq = i + 1; qq < n; ++qq) if (s.fhash[qq] == s.fhash[i]) acc = logaddexp_d(acc, s.score[qq]);
+            double acc = fin.score[i];
+            for (int qq = i + 1; qq < n; ++qq) if (fin.fhash[qq] == fin.fhash[i]) acc = logaddexp_d(acc, fin.score[qq]);
             if (LM) acc = __dadd_rn(acc, s.commit_lm[i]);
             if (acc > bs) { bs = acc; bi = i; }
         }

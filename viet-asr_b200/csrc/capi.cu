@@ -342,7 +342,10 @@ static int pick_nsub(const vasr_model* m, int B, int T_f)
     if (want < 1) want = 1;
     if (want > 8) want = 8;
     const int tiles_per_utt = ceil_div(vasr_model_out_frames(m, T_f), 128);
-    while (want > 1 && (B / want) * tiles_per_utt < 64) --want;     // keep every launch >= ~64 tiles
+    // a sub-batch must still fill the machine on its own: the persistent kernels of two sub-batches cannot share an SM
+    // (shared memory), so they only overlap at their tails.  Measured (profiles/r2_experiments.md): 128 x 5 s as 2 x 64
+    // takes 5.41 ms, as 1 x 128 3.96 ms; from 256 tiles per sub-batch on, two sub-batches win by ~2 %
+    while (want > 1 && (B / want) * tiles_per_utt < 256) --want;
     return want;
 }
 }  // namespace vasr
@@ -590,24 +593,47 @@ static int transcribe_impl(vasr_frontend* fe, vasr_model* m, const float* wave_h
     char* s = (char*)m->scratch;
     int rc;
     const int nsub = pick_nsub(m, B, T_f);
-    if (nsub < 2) {
+    // the encoder runs the batch as ONE launch chain (nsub = 1) unless every sub-batch fills the machine; the copy of
+    // the waveforms is still cut into chunks so that the front end of chunk i runs while chunk i + 1 crosses PCIe
+    const int nchunk = nsub >= 2 ? nsub : ((size_t)B * L * sizeof(float) >= ((size_t)4 << 20) ? (B < 4 ? B : 4) : 1);
+    if (nchunk >= 2 && !m->copy_stream) {
+        VASR_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        VASR_CUDA_OK(cudaEventCreateWithFlags(&m->host_start, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) {
+            VASR_CUDA_OK(cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming));
+            VASR_CUDA_OK(cudaEventCreateWithFlags(&m->ready[i], cudaEventDisableTiming));
+        }
+    }
+    if (nchunk < 2) {
         VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave, wave_host, (size_t)B * L * sizeof(float), cudaMemcpyHostToDevice, st));
         VASR_CUDA_OK(cudaMemcpyAsync(s + o_len, length_host, (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         if ((rc = vasr_frontend_forward(fe, (const float*)(s + o_wave), (const int64_t*)(s + o_len), B, L,
                                         (float*)(s + o_feat), (int64_t*)(s + o_seq), st))) return rc;
         if ((rc = vasr_encoder_forward(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
                                        (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st))) return rc;
+    } else if (nsub < 2) {
+        VASR_CUDA_OK(cudaEventRecord(m->host_start, st));                 // scratch is free once earlier work on st is done
+        VASR_CUDA_OK(cudaStreamWaitEvent(m->copy_stream, m->host_start, 0));
+        for (int h = 0; h < nchunk; ++h) {
+            const int b0 = (int)((long long)B * h / nchunk), b1 = (int)((long long)B * (h + 1) / nchunk);
+            VASR_CUDA_OK(cudaMemcpyAsync(s + o_wave + (size_t)b0 * L * sizeof(float), wave_host + (size_t)b0 * L,
+                                         (size_t)(b1 - b0) * L * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+            VASR_CUDA_OK(cudaMemcpyAsync(s + o_len + (size_t)b0 * sizeof(int64_t), length_host + b0,
+                                         (size_t)(b1 - b0) * sizeof(int64_t), cudaMemcpyHostToDevice, m->copy_stream));
+            VASR_CUDA_OK(cudaEventRecord(m->copied[h], m->copy_stream));
+        }
+        for (int h = 0; h < nchunk; ++h) {
+            const int b0 = (int)((long long)B * h / nchunk), b1 = (int)((long long)B * (h + 1) / nchunk);
+            VASR_CUDA_OK(cudaStreamWaitEvent(st, m->copied[h], 0));
+            if ((rc = vasr_frontend_forward(fe, (const float*)(s + o_wave) + (size_t)b0 * L, (const int64_t*)(s + o_len) + b0,
+                                            b1 - b0, L, (float*)(s + o_feat) + (size_t)b0 * T_f * m->feat_in,
+                                            (int64_t*)(s + o_seq) + b0, st))) return rc;
+        }
+        if ((rc = vasr_encoder_forward(m, (const float*)(s + o_feat), (const int64_t*)(s + o_seq), B, T_f,
+                                       (float*)(s + o_enc), (float*)(s + o_elen), s + o_ws, ws_b, st))) return rc;
     } else {
         // software pipeline over the encoder's sub-batches: the waveforms of sub-batch i+1 cross PCIe on a copy
         // stream while sub-batch i runs its front end (on `st`) and its encoder layers (on its sub-stream)
-        if (!m->copy_stream) {
-            VASR_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-            VASR_CUDA_OK(cudaEventCreateWithFlags(&m->host_start, cudaEventDisableTiming));
-            for (int i = 0; i < 8; ++i) {
-                VASR_CUDA_OK(cudaEventCreateWithFlags(&m->copied[i], cudaEventDisableTiming));
-                VASR_CUDA_OK(cudaEventCreateWithFlags(&m->ready[i], cudaEventDisableTiming));
-            }
-        }
         // tile counters live at the start of the encoder workspace (after the length table)
         const size_t lens_b = align_up((size_t)(m->n_stage + 1) * B * sizeof(int), 256);
         VASR_CUDA_OK(cudaMemsetAsync(s + o_ws + lens_b, 0, sync_region_bytes(m->layers.size(), B), st));
