@@ -24,6 +24,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace vasr {
@@ -32,7 +34,12 @@ namespace beam {
 constexpr int BW_MAX = 128;             // beam width limit
 constexpr int MC = 16;                  // candidate symbols per frame (blank included)
 constexpr int NC_MAX = BW_MAX * MC;     // expansion limit per frame
-constexpr int THREADS = 256;
+#ifndef VASR_BEAM_THREADS
+#define VASR_BEAM_THREADS 256
+#endif
+// 256 and 512 threads measure within 3 % of each other (512 is ahead on wide frames - 128 beams x 16 symbols -, 256 on
+// the narrow frames of real speech: fewer warps per barrier); 2 CTAs per SM either way (shared memory)
+constexpr int THREADS = VASR_BEAM_THREADS;
 constexpr unsigned long long H0 = 0x9E3779B97F4A7C15ull;
 constexpr int SYM_NONE = 255, KEY_BLANK = 254, KEY_NONE = 255;
 
@@ -47,8 +54,9 @@ __host__ __device__ __forceinline__ unsigned long long mix(unsigned long long h,
 }
 __device__ __forceinline__ double logaddexp_d(double a, double b)
 {
+    // m + log(exp(a - m) + exp(b - m)) as pyctcdecode's _log_sum_exp writes it; one of the two terms is exp(0) = 1 exactly
     const double m = fmax(a, b);
-    return m + log(exp(a - m) + exp(b - m));
+    return m + log(1.0 + exp(fmin(a, b) - m));
 }
 // order-preserving map double -> u64 (ascending)
 __device__ __forceinline__ unsigned long long dkey(double x)
@@ -171,15 +179,16 @@ struct Smem {
     int commit_ctx[BW_MAX][MAX_ORDER - 1];
     int commit_nctx[BW_MAX];
     int has_space;
-    float lp[128];
+    __align__(16) float lp[128];
     int cand[MC];
     float candp[MC];
-    int ncand, nbeam, nalive, nsurv;
+    int ncand, nbeam, nalive, nsurv, nmerge;
+    int wcnt[THREADS / 32];
     int sel_digit, sel_need, sel_cnt;    // radix select: digit of the bucket holding the beam_width-th key, what is still needed from it, its size
     unsigned int hist[256];
     double wbest[THREADS / 32];
     // by insertion index (candidate = symbol-major (cand, beam) pair)
-    union {
+    union alignas(16) {
         unsigned long long ckey[NC_MAX]; // merge key of the candidate's state (phases 2-3)
         double ucomb[NC_MAX];            // ranking score of a merged state, at its first-seen candidate (phases 4-5)
         unsigned long long surv_key[NC_MAX];    // phase 6, many states alive: the ones the radix select kept
@@ -191,15 +200,28 @@ struct Smem {
         unsigned short surv_idx[NC_MAX]; // phase 6: first-seen candidate of the states the radix select kept
     };
     unsigned short next[NC_MAX];         // next candidate in the slot's member list (EMPTY = end)
-    union {
+    unsigned short mlist[NC_MAX];        // first-seen members of the states that have more than one member
+    union alignas(16) {
         unsigned int table[TABLE_MAX];   // slot -> a member of the state stored there, in the end its FIRST-SEEN member
         unsigned long long alive_key[NC_MAX];   // after the merge: order-preserving keys of the states that survive pruning
     };
-    union {
+    union alignas(16) {
         unsigned int head[TABLE_MAX];    // slot -> most recently pushed member
         unsigned short alive_idx[NC_MAX];       // after the merge: first-seen candidate of every surviving state
     };
 };
+
+// developer builds (make dev): cycles per phase of CTA 0, printed by the launcher when VASR_BEAM_PROF is set
+#ifdef VASR_DEV
+__device__ unsigned long long g_beam_prof[16];
+#define BPROF_DECL() long long _bt = clock64(); unsigned long long _bacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define BPROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); _bacc[i] += (unsigned long long)(_n - _bt); _bt = _n; } } while (0)
+#define BPROF_FLUSH() do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int _i = 0; _i < 16; ++_i) g_beam_prof[_i] += _bacc[_i]; } while (0)
+#else
+#define BPROF_DECL() do {} while (0)
+#define BPROF(i) do {} while (0)
+#define BPROF_FLUSH() do {} while (0)
+#endif
 
 // One CTA per utterance, T_e sequential frames.  A frame is six block-wide phases (no sort):
 //   1. warp 0 clips the frame's log-probs and picks the candidate symbols; the other warps clear the merge table
@@ -213,7 +235,7 @@ struct Smem {
 //      broadcasts, A ~ 100-400 - which is the position a stable sort would give it
 //   6. ranks < beam_width become the beams of the next frame (other beam set) and write their back-pointers
 template <bool LM>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int T, int V1, int blank, int space_id, int beam_width,
             float tok_min, float prune, unsigned char* __restrict__ bp_parent, unsigned char* __restrict__ bp_sym,
             int* __restrict__ out_ids, int* __restrict__ out_len, float* __restrict__ out_score,
@@ -259,70 +281,81 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
         s.commit_lm[i] = lm_accumulate(q, c.lmscore[i], r);
     };
 
+    BPROF_DECL();
+    if (tid >= V1 && tid < 128) s.lp[tid] = -INFINITY;                     // padding of the symbol table (never rewritten)
+    float lp_next = (tid < V1 && Tb > 0) ? lpb[tid] : 0.f;                 // log-probs of the next frame, one symbol per thread
     for (int t = 0; t < Tb; ++t) {
+        BPROF(15);
         const BeamSet& cur = s.bs[t & 1];
         BeamSet& nxt = s.bs[(t & 1) ^ 1];
-        // ---- 1. frame log-probs (clipped like log(clip(p, 1e-15, 1))) and candidate symbols: warp 0 ------------
-        if (wid == 0) {
-            for (int v = lane; v < V1; v += 32) s.lp[v] = fminf(fmaxf(lpb[(size_t)t * V1 + v], clip_lo), 0.f);
-            __syncwarp();
-            // argmax, ties -> lowest index (np.argmax)
-            float best = -INFINITY; int bi = 0x7fffffff;
-            for (int v = lane; v < V1; v += 32) { const float x = s.lp[v]; if (x > best) { best = x; bi = v; } }
-            for (int o = 16; o >= 1; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            // candidates in ascending index; if more than MC qualify keep the argmax plus the MC-1 most probable
-            // others, ties to the lower index (documented kernel limit; a peaked CTC posterior never reaches it)
-            int cnt = 0;
-            for (int v0 = 0; v0 < V1; v0 += 32) {
-                const int v = v0 + lane;
-                const bool f = v < V1 && (s.lp[v] >= tok_min || v == bi);
-                cnt += __popc(__ballot_sync(0xffffffffu, f));
-            }
-            const bool capped = cnt > MC;
-            auto selected = [&](int v) -> bool {
-                if (v >= V1) return false;
-                if (v == bi) return true;
-                const float x = s.lp[v];
-                if (x < tok_min) return false;
-                if (!capped) return true;
-                int rank = 0;                          // qualifying non-argmax symbols ahead of v
-                for (int u = 0; u < V1; ++u) {
-                    const float y = s.lp[u];
-                    if (u != bi && y >= tok_min && (y > x || (y == x && u < v))) ++rank;
-                }
-                return rank < MC - 1;
-            };
-            int base = 0; bool sp = false;
-            for (int v0 = 0; v0 < V1; v0 += 32) {
-                const int v = v0 + lane;
-                const bool f = selected(v);
-                const unsigned m = __ballot_sync(0xffffffffu, f);
-                if (f) { const int p = base + __popc(m & ((1u << lane) - 1u)); s.cand[p] = v; s.candp[p] = s.lp[v]; }
-                sp = sp || (__ballot_sync(0xffffffffu, f && v == space_id) != 0u);
-                base += __popc(m);
-            }
-            if (lane == 0) { s.ncand = base; s.has_space = sp ? 1 : 0; s.nalive = 0; s.nsurv = 0; }
-        } else {
-            // the other warps clear the part of the merge table this frame can touch (2 x the next power of two of
-            // nbeam * MC bounds 2 x Np below)
+        // ---- 1. frame log-probs (clipped like log(clip(p, 1e-15, 1))) and candidate symbols --------------------
+        // thread v owns symbol v.  The argmax (ties -> lowest index, np.argmax) is always a candidate; the others need
+        // logp >= token_min_logp, and if more than MC symbols qualify only the argmax and the MC - 1 most probable
+        // others are kept, ties to the lower index (documented kernel limit; a peaked CTC posterior never reaches it).
+        // Every thread ranks its own symbol against the V1 others on shared-memory broadcasts.
+        if (tid < V1) s.lp[tid] = fminf(fmaxf(lp_next, clip_lo), 0.f);
+        if (tid < V1 && t + 1 < Tb) lp_next = lpb[(size_t)(t + 1) * V1 + tid];      // in flight during this frame
+        if (tid == 0) { s.nalive = 0; s.nsurv = 0; s.nmerge = 0; s.has_space = 0; }
+        {
+            // clear the part of the merge table this frame can touch (2 x the next power of two of nbeam * MC
+            // bounds 2 x Np below)
             int cap = 1; while (cap < s.nbeam * MC) cap <<= 1;
             cap *= 2;
             const uint4 e4 = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
             uint4* t4 = reinterpret_cast<uint4*>(s.table);
             uint4* h4 = reinterpret_cast<uint4*>(s.head);
-            for (int i = tid - 32; i < cap / 4; i += THREADS - 32) { t4[i] = e4; h4[i] = e4; }
+            for (int i = tid; i < cap / 4; i += THREADS) { t4[i] = e4; h4[i] = e4; }
         }
         __syncthreads();
+        BPROF(0);
+        // symbols with logp >= token_min_logp; when there are between 1 and MC of them they ARE the candidates (the
+        // argmax is one of them) and nothing has to be ranked - the usual case on speech
+        float x = -INFINITY;
+        if (tid < V1) x = s.lp[tid];
+        const bool qual = tid < V1 && x >= tok_min;
+        const int Q = __syncthreads_count(qual ? 1 : 0);
+        bool sel = qual;
+        if (Q < 1 || Q > MC) {
+            sel = false;
+            if (tid < V1 && (qual || Q < 1)) {
+                int bf[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};   // symbols that precede this one in (logp descending, index ascending) order
+                const float4* lp4 = reinterpret_cast<const float4*>(s.lp);       // entries [V1, 128) are -inf: they precede nothing
+                for (int u4 = 0; u4 < (V1 + 3) / 4; ++u4) {
+                    const float4 y4 = lp4[u4];
+                    const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool prec = (y[j] > x) || (y[j] == x && u4 * 4 + j < tid);
+                        bf[j] += prec ? 1 : 0;
+                        bq[j] += (prec && y[j] >= tok_min) ? 1 : 0;
+                    }
+                }
+                const int before = bf[0] + bf[1] + bf[2] + bf[3], before_q = bq[0] + bq[1] + bq[2] + bq[3];
+                // before == 0: the argmax.  Otherwise before_q counts the argmax too (it qualifies whenever anything does)
+                sel = before == 0 || (qual && before_q <= MC - 1);
+            }
+        }
+        BPROF(1);
+        const unsigned selbal = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) s.wcnt[wid] = __popc(selbal);
+        if (sel && tid == space_id) s.has_space = 1;
+        __syncthreads();
+        BPROF(2);
+        if (sel) {                                 // candidates in ascending index
+            int pos = __popc(selbal & ((1u << lane) - 1u));
+            for (int w = 0; w < wid; ++w) pos += s.wcnt[w];
+            s.cand[pos] = tid; s.candp[pos] = x;
+        }
+        if (tid == 0) { int c = 0; for (int w = 0; w < THREADS / 32; ++w) c += s.wcnt[w]; s.ncand = c; }
+        __syncthreads();
+        BPROF(3);
         const int n = s.nbeam, m = s.ncand, N = n * m;
         int Np = 1; while (Np < N) Np <<= 1;
         const unsigned mask = (unsigned)(2 * Np - 1);
 
         // ---- 2. LM: score the word every beam would commit on ' ' (once per beam and frame) --------------------
         if (LM && s.has_space && tid < n && cur.wplen[tid] > 0) commit_word(cur, tid, false);
+        BPROF(4);
 
         // ---- 2. expansion, insertion index = cand * n + beam (symbol-major like the reference loop) ------------
         for (int idx = tid; idx < N; idx += THREADS) {
@@ -342,8 +375,12 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
             s.cmeta[idx] = (unsigned)i | ((unsigned)app << 8) | ((unsigned)nls << 16) | ((unsigned)nlk << 24);
         }
         __syncthreads();
+        BPROF(5);
 
         // ---- 3. merge equal states: insert into the table; the slot ends up holding the first-seen member -------
+        // (a plain read first: members that join an existing state - and every probe past an occupied slot - cost no
+        // atomic; the shared-memory atomics are what bounds this phase.  Issuing a thread's candidates as a batch of
+        // unconditional atomicCAS was measured 40 % slower, profiles/r2_experiments.md)
         for (int idx = tid; idx < N; idx += THREADS) {
             const unsigned long long key = s.ckey[idx];
             unsigned p = (unsigned)(key >> 20) & mask;
@@ -360,14 +397,37 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
             s.next[idx] = (unsigned short)atomicExch(&s.head[p], (unsigned)idx);
         }
         __syncthreads();
+        BPROF(6);
 
         // ---- 4. first-seen members: log-sum-exp of the members in insertion order, ranking score ----------------
+        // ranking score: acoustic, plus lm(text) and the partial-word penalty of the state when an LM is fused
+        auto finish = [&](int idx, double acc) -> double {
+            double comb = acc;
+            if (LM) {
+                const unsigned meta = s.cmeta[idx];
+                const int src = meta & 0xff, app = (meta >> 8) & 0xff;
+                double lmv; int wl;
+                if (app == space_id) { lmv = s.commit_lm[src]; wl = 0; }
+                else { lmv = cur.lmscore[src]; wl = cur.wplen[src] + (app != SYM_NONE ? 1 : 0); }
+                comb = __dadd_rn(acc, __dadd_rn(lmv, partial_penalty(q, wl)));
+            }
+            s.ucomb[idx] = comb;
+            return comb;
+        };
         unsigned own = 0;                                                  // bit k: candidate tid + k * THREADS is a first-seen member
         double best = -INFINITY;
         for (int idx = tid, k = 0; idx < N; idx += THREADS, ++k) {
             const unsigned p = s.cslot[idx];
             if (s.table[p] != (unsigned)idx) continue;
             own |= 1u << k;
+            if (s.head[p] == (unsigned)idx && s.next[idx] == EMPTY) best = fmax(best, finish(idx, s.cscore[idx]));   // the only member
+            else s.mlist[atomicAdd(&s.nmerge, 1)] = (unsigned short)idx;    // several members: the float64 log-sum-exp chains are
+        }                                                                   // spread evenly over the threads below
+        __syncthreads();
+        const int M = s.nmerge;
+        for (int w = tid; w < M; w += THREADS) {
+            const int idx = s.mlist[w];
+            const unsigned p = s.cslot[idx];
             double acc = s.cscore[idx];
             int last = idx;
             while (true) {                                                 // next member in ascending insertion index
@@ -379,24 +439,14 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
                 last = pick;
             }
             s.cscore[idx] = acc;
-            // ranking score: acoustic, plus lm(text) and the partial-word penalty of the state when an LM is fused
-            double comb = acc;
-            if (LM) {
-                const unsigned meta = s.cmeta[idx];
-                const int src = meta & 0xff, app = (meta >> 8) & 0xff;
-                double lmv; int wl;
-                if (app == space_id) { lmv = s.commit_lm[src]; wl = 0; }
-                else { lmv = cur.lmscore[src]; wl = cur.wplen[src] + (app != SYM_NONE ? 1 : 0); }
-                comb = __dadd_rn(acc, __dadd_rn(lmv, partial_penalty(q, wl)));
-            }
-            s.ucomb[idx] = comb;
-            best = fmax(best, comb);
+            best = fmax(best, finish(idx, acc));
         }
         for (int o = 16; o >= 1; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
         if (lane == 0) s.wbest[wid] = best;
         __syncthreads();
         best = s.wbest[0];
         for (int w = 1; w < THREADS / 32; ++w) best = fmax(best, s.wbest[w]);
+        BPROF(7);
 
         // ---- 5. prune at best + beam_prune_logp -----------------------------------------------------------------
         const double thr = best + (double)prune;
@@ -410,27 +460,26 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
             }
         }
         __syncthreads();
+        BPROF(8);
 
         // ---- 6. rank by (score descending, first-seen ascending); the beam_width best become the new beams ------
         const int A = s.nalive;
-        const unsigned long long* rkey = s.alive_key;
-        const unsigned short* ridx = s.alive_idx;
-        int R = A;
-        if (A > 2 * BW_MAX) {
+        const bool many = A > 2 * BW_MAX;
+        if (many) {
             // many states alive (diffuse posteriors): counting ranks among all of them is O(A^2).  Radix-select the
             // key of the beam_width-th best state first, 8 bits at a time from the highest bit in which the alive
             // keys can differ (they all lie between the keys of thr and best), and rank only the states at or above
             // it.  The select stops as soon as the bucket that holds the beam_width-th key plus everything above it
-            // is at most 2 x BW_MAX states; states with equal scores stay together, the counting below orders them.
+            // is at most beam_width + 32 states; states with equal scores stay together, the counting below orders them.
             const unsigned long long kbest = dkey(best), kthr = dkey(thr);
             const int hb = 63 - __clzll((long long)(kbest ^ kthr));         // -1: all alive keys are equal
             int shift = hb < 0 ? -8 : (hb / 8) * 8;
             unsigned long long pmask = shift >= 56 ? 0ull : (~0ull << (shift + 8));
             unsigned long long prefix = kbest & pmask;
-            static_assert(THREADS == 256, "one histogram bin per thread");
+            static_assert(THREADS >= 256, "one histogram bin per thread");
             if (tid == 0) s.sel_need = beam_width;
             for (; shift >= 0; shift -= 8) {
-                s.hist[tid] = 0u;
+                if (tid < 256) s.hist[tid] = 0u;
                 __syncthreads();
                 for (int a = tid; a < A; a += THREADS) {
                     const unsigned long long ka = s.alive_key[a];
@@ -461,7 +510,7 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
                 __syncthreads();
                 prefix |= (unsigned long long)s.sel_digit << shift;
                 pmask |= 0xFFull << shift;
-                if ((beam_width - s.sel_need) + s.sel_cnt <= 2 * BW_MAX) break;
+                if ((beam_width - s.sel_need) + s.sel_cnt <= beam_width + 32) break;
             }
             for (int a = tid; a < A; a += THREADS) {
                 const unsigned long long ka = s.alive_key[a];
@@ -472,17 +521,25 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
                 }
             }
             __syncthreads();
-            rkey = s.surv_key; ridx = s.surv_idx; R = s.nsurv;
         }
+        BPROF(9);
+        auto rank_and_fill = [&](const unsigned long long* rkey, const unsigned short* ridx, const int R) {
         for (int a = tid; a < R; a += THREADS) {
             const unsigned long long ka = rkey[a];
             const unsigned ia = ridx[a];
-            int k = 0;
-            for (int o = 0; o < R; ++o) {
-                const unsigned long long ko = rkey[o];
-                const unsigned io = ridx[o];
-                k += (ko > ka || (ko == ka && io < ia)) ? 1 : 0;
+            // states ahead of this one: larger key, or equal key and seen earlier.  Equal float64 scores are rare, so the
+            // main loop only counts larger and equal keys (two keys per 16-byte load, independent counters)
+            int g0 = 0, g1 = 0, e0 = 0, e1 = 0;
+            const ulonglong2* rk2 = reinterpret_cast<const ulonglong2*>(rkey);
+            for (int o = 0; o < R / 2; ++o) {
+                const ulonglong2 kk = rk2[o];
+                g0 += kk.x > ka ? 1 : 0; e0 += kk.x == ka ? 1 : 0;
+                g1 += kk.y > ka ? 1 : 0; e1 += kk.y == ka ? 1 : 0;
             }
+            if (R & 1) { const unsigned long long ko = rkey[R - 1]; g0 += ko > ka ? 1 : 0; e0 += ko == ka ? 1 : 0; }
+            int k = g0 + g1;
+            if (e0 + e1 > 1)
+                for (int o = 0; o < R; ++o) k += (rkey[o] == ka && ridx[o] < ia) ? 1 : 0;
             if (k >= beam_width) continue;
             const unsigned meta = s.cmeta[ia];
             const int src = meta & 0xff, app = (meta >> 8) & 0xff;
@@ -509,9 +566,15 @@ beam_kernel(const float* __restrict__ logp, const int* __restrict__ frames, int 
             bpp[(size_t)t * BW_MAX + k] = (unsigned char)src;
             bps[(size_t)t * BW_MAX + k] = (unsigned char)app;
         }
+        };
+        if (many) rank_and_fill(s.surv_key, s.surv_idx, s.nsurv);
+        else rank_and_fill(s.alive_key, s.alive_idx, A);
+        BPROF(10);
         if (tid == 0) s.nbeam = A < beam_width ? A : beam_width;
         __syncthreads();
+        BPROF(11);
     }
+    BPROF_FLUSH();
     const BeamSet& fin = s.bs[Tb & 1];
 
     // ---- end of utterance: the partial word joins the text; states with equal text merge (first-seen order);
@@ -704,6 +767,18 @@ static int beam_launch(const float* log_probs, const int32_t* frames, int B, int
                                                      beam_prune_logp, bp_parent, bp_sym, out_ids, out_len, out_score, DeviceLM{}, q);
     }
     VASR_LAUNCH_OK("beam_kernel");
+#ifdef VASR_DEV
+    if (getenv("VASR_BEAM_PROF")) {
+        unsigned long long h[16], z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_beam_prof, sizeof(h));
+        cudaMemcpyToSymbol(g_beam_prof, z, sizeof(z));
+        fprintf(stderr, "BEAMPROF B=%d T=%d lm=%d | kcycles of CTA 0: lp+clear %llu symbol-rank %llu sync %llu cand-list %llu | lm-commit %llu expand %llu insert %llu "
+                        "merge %llu prune %llu select %llu rank+fill %llu end-sync %llu\n",
+                B, T, lm ? 1 : 0, h[0] / 1000, h[1] / 1000, h[2] / 1000, h[3] / 1000, h[4] / 1000, h[5] / 1000, h[6] / 1000, h[7] / 1000,
+                h[8] / 1000, h[9] / 1000, h[10] / 1000, h[11] / 1000);
+    }
+#endif
     return VASR_OK;
 }
 
