@@ -2,10 +2,10 @@
 //   * lens_kernel      - sequence-length chain of MaskedConv1d.get_seq_len (parts/jasper.py:108-111)
 //   * dw_conv_kernel   - depthwise conv (groups = C) with register sliding window
 //   * pw_gemm_kernel   - 1x1 conv as an fp32 SGEMM with the BN shift / residual GEMM / ReLU /
-//                        length mask fused in the epilogue; a second epilogue computes the CTC
-//                        decoder's bias + log-softmax + greedy argmax (jasper.py:253-254,
-//                        greedy_ctc_decoder.py:35)
-// These are the exact-order fp32 path (VASR_GEMM_FP32_SIMT) and the oracle the tcgen05 path is
+//                        length mask fused in the epilogue
+//   * decoder_kernel   - the CTC head: skinny fp32 GEMM (cp.async double-buffered) + bias + log-softmax +
+//                        greedy argmax (jasper.py:253-254, greedy_ctc_decoder.py:35); used by every gemm mode
+// lens/dw_conv/pw_gemm are the exact-order fp32 path (VASR_GEMM_FP32_SIMT) and the oracle the tcgen05 path is
 // debugged against on the device.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -135,7 +135,7 @@ int launch_dw_conv(const float* x, const float* w, float* y, int B, int C, int T
 // ---------------------------------------------------------------------------------------------
 constexpr int GM = 128, GN = 128, GK = 16, GLD = GM + 4;
 
-enum { EPI_CONV = 0, EPI_DECODER = 1 };
+enum { EPI_CONV = 0 };
 
 struct PwArgs {
     const float* X; const float* W; int Cin;
@@ -144,8 +144,6 @@ struct PwArgs {
     float* Y; int N; int Cout; int T;              // rows N = B*T
     const int* len;                                // [B] valid frames (mask) or null
     int relu; int mask_tail;                       // mask_tail: zero rows t >= len[b]
-    // decoder epilogue
-    float* logp; long long* ids;
 };
 
 template <int TN>
@@ -190,8 +188,7 @@ __device__ __forceinline__ void gemm_accumulate(const float* __restrict__ A, int
     }
 }
 
-// TN = output columns per thread: CTA tile = 128 rows x 16*TN columns (8 for the convs; the decoder picks the
-// smallest of {2, 4, 8} that covers its V+1 classes so a 29-class head does not pay for 128 columns)
+// TN = output columns per thread: CTA tile = 128 rows x 16*TN columns
 template <int EPI, int TN>
 __global__ void __launch_bounds__(256)
 pw_gemm_kernel(PwArgs p)
@@ -211,7 +208,7 @@ pw_gemm_kernel(PwArgs p)
     gemm_accumulate<TN>(p.X, p.Cin, p.N, row0, p.W, p.Cin, p.Cout, col0, p.Cin, acc, As, Bs);
     if (p.R) gemm_accumulate<TN>(p.R, p.Cres, p.N, row0, p.Wr, p.Cres, p.Cout, col0, p.Cres, acc, As, Bs);
 
-    if constexpr (EPI == EPI_CONV) {
+    {
         static_assert(TN == 8, "conv epilogue is written for 8 columns per thread");
         float sh[8];
 #pragma unroll
@@ -245,57 +242,6 @@ pw_gemm_kernel(PwArgs p)
                     if (col0 + tx * 8 + j < p.Cout) yrow[j] = v[j];
             }
         }
-    } else {
-        // decoder: the whole class row (Cout <= 16*TN) lives in the 16 lanes sharing `ty`
-        float bias[TN];
-#pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int co = tx * TN + j;
-            bias[j] = (co < p.Cout) ? __ldg(p.shift + co) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int n = row0 + ty * 8 + i;
-            float v[TN];
-            float mx = -FLT_MAX;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                v[j] = acc[i][j] + bias[j];
-                if (tx * TN + j < p.Cout) mx = fmaxf(mx, v[j]);
-            }
-#pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float se = 0.f;
-#pragma unroll
-            for (int j = 0; j < TN; ++j)
-                if (tx * TN + j < p.Cout) se += expf(v[j] - mx);
-#pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-            const float lse = logf(se);
-            // greedy argmax over the log-probs, ties -> lowest index (torch.argmax)
-            float best = -FLT_MAX; int bi = 0x7fffffff;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                v[j] = (v[j] - mx) - lse;
-                const int co = tx * TN + j;
-                if (co < p.Cout && (v[j] > best)) { best = v[j]; bi = co; }
-            }
-#pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (n < p.N) {
-                if (p.logp) {
-                    float* lrow = p.logp + (size_t)n * p.Cout + tx * TN;
-#pragma unroll
-                    for (int j = 0; j < TN; ++j)
-                        if (tx * TN + j < p.Cout) lrow[j] = v[j];
-                }
-                if (p.ids && tx == 0) p.ids[n] = (long long)bi;
-            }
-        }
     }
 }
 
@@ -314,20 +260,159 @@ int launch_pw_gemm(const float* X, const float* W, int Cin, const float* R, cons
     return VASR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTC decoder head: logits = enc[N, Cin] x W[V1, Cin]^T + bias, log-softmax over the V1 classes, greedy argmax
+// (JasperDecoderForCTC.forward, jasper.py:253-254; greedy_ctc_decoder.py:35).  A skinny fp32 GEMM (V1 = 29 ... 128
+// columns): CTA = RM*16 rows x TN*16 columns, K in chunks of 32 through a 2-stage cp.async ring (the loads of chunk
+// k + 1 are in flight while chunk k is multiplied), operands K-major in shared memory with a 4-float pad so that the
+// 16-byte loads along k are conflict-free.  Every accumulator sums its products in ascending k, like pw_gemm_kernel.
+// Thread (ty, tx): rows ty*RM + i, classes tx + 16*j  ->  a class row lives in the 16 lanes that share ty.
+// ---------------------------------------------------------------------------------------------
+constexpr int DK = 32, DLD = DK + 4;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 16 : 0;                          // 0 source bytes: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+template <int TN, int RM>
+__global__ void __launch_bounds__(256, TN <= 2 ? 4 : (TN <= 4 ? 3 : 2))
+decoder_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+               int Cin, int V1, int N, float* __restrict__ logp, long long* __restrict__ ids)
+{
+    constexpr int DM = 16 * RM, DN = 16 * TN;
+    extern __shared__ __align__(16) float dsm[];
+    float* As = dsm;                               // [2][DM][DLD]
+    float* Bs = dsm + 2 * DM * DLD;                // [2][DN][DLD]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int row0 = blockIdx.x * DM;
+
+    auto load_stage = [&](int buf, int k0) {
+        for (int c = tid; c < DM * (DK / 4); c += 256) {
+            const int r = c >> 3, q = c & 7;
+            const bool ok = row0 + r < N;
+            cp_async16(As + ((size_t)buf * DM + r) * DLD + q * 4, X + (size_t)(ok ? row0 + r : 0) * Cin + k0 + q * 4, ok);
+        }
+        for (int c = tid; c < DN * (DK / 4); c += 256) {
+            const int r = c >> 3, q = c & 7;
+            const bool ok = r < V1;
+            cp_async16(Bs + ((size_t)buf * DN + r) * DLD + q * 4, W + (size_t)(ok ? r : 0) * Cin + k0 + q * 4, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[RM][TN];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nk = Cin / DK;
+    load_stage(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                       // chunk kt has landed; chunk kt - 1's buffer is free
+        if (kt + 1 < nk) load_stage((kt + 1) & 1, (kt + 1) * DK);
+        const float* Ab = As + (size_t)(kt & 1) * DM * DLD + (size_t)ty * RM * DLD;
+        const float* Bb = Bs + (size_t)(kt & 1) * DN * DLD + (size_t)tx * DLD;
+#pragma unroll
+        for (int k4 = 0; k4 < DK / 4; ++k4) {
+            float4 a[RM], b[TN];
+#pragma unroll
+            for (int i = 0; i < RM; ++i) a[i] = *reinterpret_cast<const float4*>(Ab + i * DLD + k4 * 4);
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Bb + (size_t)j * 16 * DLD + k4 * 4);
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+                }
+        }
+    }
+
+    // epilogue: bias, log-softmax over the class row (16 lanes x TN), greedy argmax (ties -> lowest index, torch.argmax)
+    float bs[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int co = tx + 16 * j;
+        bs[j] = (co < V1) ? __ldg(bias + co) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const int n = row0 + ty * RM + i;
+        float v[TN];
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            v[j] = acc[i][j] + bs[j];
+            if (tx + 16 * j < V1) mx = fmaxf(mx, v[j]);
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+            if (tx + 16 * j < V1) se += expf(v[j] - mx);
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        const float lse = logf(se);
+        float best = -FLT_MAX; int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            v[j] = (v[j] - mx) - lse;
+            const int co = tx + 16 * j;
+            if (co < V1 && (v[j] > best)) { best = v[j]; bi = co; }
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (n < N) {
+            if (logp) {
+                float* lrow = logp + (size_t)n * V1;
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (tx + 16 * j < V1) lrow[tx + 16 * j] = v[j];
+            }
+            if (ids && tx == 0) ids[n] = (long long)bi;
+        }
+    }
+}
+
+template <int TN, int RM>
+static int launch_decoder_t(const float* enc, const float* W, const float* bias, int Cin, int V1, int N, float* logp,
+                            long long* ids, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)2 * (16 * RM + 16 * TN) * DLD * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VASR_CUDA_OK(cudaFuncSetAttribute(decoder_kernel<TN, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    decoder_kernel<TN, RM><<<ceil_div(N, 16 * RM), 256, smem, st>>>(enc, W, bias, Cin, V1, N, logp, ids);
+    VASR_LAUNCH_OK("decoder_kernel");
+    return VASR_OK;
+}
+
 int launch_decoder(const float* enc, const float* W, const float* bias, int Cin, int V1,
                    int N, float* logp, long long* ids, cudaStream_t st)
 {
     VASR_REQUIRE(V1 <= GN, "decoder: at most %d classes (incl. blank) are supported (got %d)", GN, V1);
-    VASR_REQUIRE(Cin % GK == 0, "decoder: feat_in must be a multiple of %d (got %d)", GK, Cin);
-    PwArgs p{};
-    p.X = enc; p.W = W; p.Cin = Cin; p.shift = bias; p.N = N; p.Cout = V1; p.T = 1;
-    p.logp = logp; p.ids = ids;
-    dim3 grid(ceil_div(N, GM), 1);
-    if (V1 <= 32) pw_gemm_kernel<EPI_DECODER, 2><<<grid, 256, 0, st>>>(p);
-    else if (V1 <= 64) pw_gemm_kernel<EPI_DECODER, 4><<<grid, 256, 0, st>>>(p);
-    else pw_gemm_kernel<EPI_DECODER, 8><<<grid, 256, 0, st>>>(p);
-    VASR_LAUNCH_OK("pw_gemm_kernel<decoder>");
-    return VASR_OK;
+    VASR_REQUIRE(Cin % DK == 0, "decoder: feat_in must be a multiple of %d (got %d)", DK, Cin);
+    // 64-row CTAs (4 rows per thread): <= 64 registers at TN = 2, i.e. 4 CTAs per SM.  128-row CTAs (8 rows per
+    // thread, a better FMA : shared-load ratio) need 128 registers -> 2 CTAs per SM and 1.7 waves on 256 x 5 s:
+    // measured 0.167 ms against 0.217 ms for the round-1 kernel
+    if (V1 <= 32) return launch_decoder_t<2, 4>(enc, W, bias, Cin, V1, N, logp, ids, st);
+    if (V1 <= 64) return launch_decoder_t<4, 4>(enc, W, bias, Cin, V1, N, logp, ids, st);
+    return launch_decoder_t<8, 4>(enc, W, bias, Cin, V1, N, logp, ids, st);
 }
 
 int launch_lens(const long long* seq_len, int B, int b0, int nb, int n_stage, const int* st_k, const int* st_s,

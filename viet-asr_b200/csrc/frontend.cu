@@ -197,16 +197,18 @@ stft_mel_kernel(const float* __restrict__ wave, const long long* __restrict__ le
     }
 }
 
-// K2: one CTA per utterance. mean / unbiased std over t < seq, (x-mean)/(std+1e-5), zero t >= seq.
-__global__ void __launch_bounds__(256)
+// K2: one CTA of 1024 threads per utterance (thread = mel bin x time phase; 256 threads left the two dependent
+// passes latency-bound).  mean / unbiased std over t < seq, (x-mean)/(std+1e-5), zero t >= seq.
+constexpr int NORM_THREADS = 1024;
+__global__ void __launch_bounds__(NORM_THREADS)
 normalize_kernel(float* __restrict__ feat, const long long* __restrict__ length, long long* __restrict__ seq_out,
                  int T_frames, int T_out, int nfilt, int hop)
 {
-    __shared__ float red[256];
+    __shared__ float red[NORM_THREADS];
     __shared__ float s_mean[128], s_std[128];
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
-    const int phases = 256 / nfilt;
+    const int phases = NORM_THREADS / nfilt;
     const int j = tid % nfilt, ph = tid / nfilt;
     // seq = ceil(float(len) / hop) (features.py:238-239, float32 arithmetic like torch)
     const float lenf = (float)length[b];
@@ -345,7 +347,7 @@ extern "C" int vasr_frontend_forward(vasr_frontend* fe, const float* wave, const
         fe->d_mel_w, fe->max_nz, fe->cfg.nfilt, fe->cfg.n_window_size, hop, fe->cfg.preemph,
         fe->cfg.log_zero_guard, feat);
     VASR_LAUNCH_OK("stft_mel_kernel");
-    normalize_kernel<<<B, 256, 0, st>>>(feat, (const long long*)length, (long long*)seq_len,
+    normalize_kernel<<<B, NORM_THREADS, 0, st>>>(feat, (const long long*)length, (long long*)seq_len,
                                         T_frames, T_out, fe->cfg.nfilt, hop);
     VASR_LAUNCH_OK("normalize_kernel");
     return VASR_OK;
