@@ -601,8 +601,9 @@ def main():
     if beam:
         decode_info = {"kernel": "beam_kernel<LM>" if eng.beam.lm is not None else "beam_kernel<no LM>", "ms": search_ms_avg,
                        "share_of_step": search_ms_avg / ms_per_step, "beam_width": cfg["beam"], "frames": T_e,
-                       "bound": "latency: one CTA per utterance, T_e strictly dependent frame steps (candidate expansion, bitonic merge, "
-                                "prune); B CTAs on 148 SMs", "us_per_frame": search_ms_avg * 1e3 / T_e}
+                       "bound": "latency: one CTA per utterance (two per SM), T_e strictly dependent frames of 6-9 block barriers each "
+                                "(candidate expansion, hash-table merge in shared memory, prune, radix select + rank by counting)",
+                       "us_per_frame": search_ms_avg * 1e3 / T_e}
     line = {
         "metric": f"audio-seconds/sec (RTF^-1) {MODEL_NAME[cfg['model']]} 16kHz", "value": value, "unit": "audio-s/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "p50_ms": statistics.median(step_ms),
