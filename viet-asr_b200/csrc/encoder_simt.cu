@@ -292,13 +292,13 @@ decoder_kernel(const float* __restrict__ X, const float* __restrict__ W, const f
     auto load_stage = [&](int buf, int k0) {
         for (int c = tid; c < DM * (DK / 4); c += 256) {
             const int r = c >> 3, q = c & 7;
-            const bool ok = row0 + r < N;
-            cp_async16(As + ((size_t)buf * DM + r) * DLD + q * 4, X + (size_t)(ok ? row0 + r : 0) * Cin + k0 + q * 4, ok);
+            const bool ok = row0 + r < N && k0 + q * 4 < Cin;          // rows past N and the K tail are zero-filled
+            cp_async16(As + ((size_t)buf * DM + r) * DLD + q * 4, X + (ok ? (size_t)(row0 + r) * Cin + k0 + q * 4 : 0), ok);
         }
         for (int c = tid; c < DN * (DK / 4); c += 256) {
             const int r = c >> 3, q = c & 7;
-            const bool ok = r < V1;
-            cp_async16(Bs + ((size_t)buf * DN + r) * DLD + q * 4, W + (size_t)(ok ? r : 0) * Cin + k0 + q * 4, ok);
+            const bool ok = r < V1 && k0 + q * 4 < Cin;
+            cp_async16(Bs + ((size_t)buf * DN + r) * DLD + q * 4, W + (ok ? (size_t)r * Cin + k0 + q * 4 : 0), ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -309,7 +309,7 @@ decoder_kernel(const float* __restrict__ X, const float* __restrict__ W, const f
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    const int nk = Cin / DK;
+    const int nk = (Cin + DK - 1) / DK;
     load_stage(0, 0);
     for (int kt = 0; kt < nk; ++kt) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -406,7 +406,7 @@ int launch_decoder(const float* enc, const float* W, const float* bias, int Cin,
                    int N, float* logp, long long* ids, cudaStream_t st)
 {
     VASR_REQUIRE(V1 <= GN, "decoder: at most %d classes (incl. blank) are supported (got %d)", GN, V1);
-    VASR_REQUIRE(Cin % DK == 0, "decoder: feat_in must be a multiple of %d (got %d)", DK, Cin);
+    VASR_REQUIRE(Cin % GK == 0, "decoder: feat_in must be a multiple of %d (got %d)", GK, Cin);     // (the kernel needs 4)
     // 64-row CTAs (4 rows per thread): <= 64 registers at TN = 2, i.e. 4 CTAs per SM.  128-row CTAs (8 rows per
     // thread, a better FMA : shared-load ratio) need 128 registers -> 2 CTAs per SM and 1.7 waves on 256 x 5 s:
     // measured 0.167 ms against 0.217 ms for the round-1 kernel
