@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "viet-asr_b200", "libvasr_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 KEY = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCATOMSWS", "SYNCS", "FFMA2", "FFMA", "FMNMX", "LDS", "STS", "F2FP",
-       "HADD2", "FADD", "ATOMG", "MEMBAR", "FENCE", "UCGABAR_ARV", "BAR", "STL", "LDL", "HMMA"]
+       "HADD2", "FADD", "ATOMG", "ATOMS", "LDGSTS", "MEMBAR", "FENCE", "UCGABAR_ARV", "BAR", "STL", "LDL", "HMMA"]
 fn = None
 hist = collections.OrderedDict()
 for line in out.splitlines():
@@ -28,7 +28,7 @@ for line in out.splitlines():
             hist[fn][m.group(1) + m.group(2)] += 1
 print(f"# cuobjdump -sass {os.path.relpath(lib, ROOT)}: instructions per kernel (static counts), selected opcodes")
 for fn, h in hist.items():
-    if not any(k in fn for k in ("segment", "subblock", "stft_mel", "normalize", "beam_kernel", "ctc_collapse", "pw_gemm", "resample")):
+    if not any(k in fn for k in ("segment", "subblock", "stft_mel", "normalize", "beam_kernel", "ctc_collapse", "pw_gemm", "decoder_kernel", "resample")):
         continue
     tot = sum(v for k, v in h.items() if "." not in k)
     cells = [f"{k}={h[k]}" for k in KEY if h.get(k)]
