@@ -12,7 +12,7 @@ from oracle import quartznet_oracle as O
 pytestmark = pytest.mark.gpu
 
 LOGIT_REL = 1e-3      # north_star: "encoder logits within 1e-3 rel fp32"
-FEAT_ATOL = 2e-3      # normalised log-mel features are O(1); fp32 FFT orders differ
+FEAT_ATOL = 2e-3      # normalised log-mel features are O(1); fp32 FFT orders differ (the reference itself sits 5e-5 .. 9e-5 from float64: test_oracle_cpu.py::test_feature_noise_floor_of_the_reference_itself)
 
 
 def _cuda():
